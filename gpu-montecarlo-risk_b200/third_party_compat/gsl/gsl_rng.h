@@ -1,0 +1,2 @@
+/* GSL-subset compat: see gsl_compat_core.h */
+#include "gsl_compat_core.h"
