@@ -1,0 +1,531 @@
+// C ABI of libmcr_b200.so (declared in include/mcr_b200.h).
+//
+// Host-side orchestration only: model upload (fp64 -> packed fp32 constant layout + fp64
+// column-major copy for the fix-up), kernel selection, chunked launches
+//   [ffma_path_kernel | exact_kernel] -> exact_kernel(fix-up list) -> finalize_kernel
+// on one stream, and the reference's statistics (serial.c:152-158).  No CPU compute fallback.
+#include "../../include/mcr_b200.h"
+#include "mcr_internal.h"
+#include "mcr_engine.h"
+#include "mcr_rng.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace mcr {
+
+// ---- error reporting ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+// ---- variant registry ----------------------------------------------------------------------------
+VariantRegistry& registry() {
+    static VariantRegistry r;
+    return r;
+}
+void register_variant(const FfmaVariant& v) {
+    VariantRegistry& r = registry();
+    if (r.n < MAX_VARIANTS) r.v[r.n++] = v;
+}
+static void ensure_registered() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        register_group0(); register_group1(); register_group2(); register_group3();
+        register_group4(); register_group5(); register_group6(); register_group7();
+    });
+}
+// smallest instantiation that can run an N-asset model; a lower-triangular model may also use a
+// dense instantiation (zeros are stored), never the other way round.
+static int find_variant(int N, bool lower, bool normals) {
+    const VariantRegistry& r = registry();
+    int best = -1;
+    for (int i = 0; i < r.n; ++i) {
+        const FfmaVariant& v = r.v[i];
+        if (v.normals != normals || v.NT < N) continue;
+        if (!lower && v.lower) continue;
+        if (best < 0 || v.NT < r.v[best].NT || (v.NT == r.v[best].NT && v.lower && !r.v[best].lower)) best = i;
+    }
+    return best;
+}
+
+// which (model generation, variant) currently sits in each constant storage of each device
+struct ConstState { uint64_t gen = 0; int variant = -1; uint64_t c_gen = 0; int c_variant = -1; double c_x = 0; };
+static std::mutex g_const_mu;
+static std::map<std::pair<int, const void*>, ConstState> g_const_state;
+static std::atomic<uint64_t> g_next_gen{1};
+
+
+}  // namespace mcr
+
+using namespace mcr;
+
+
+static int set_device(const mcr_engine* e) {
+    MCR_CUDA(cudaSetDevice(e->device));
+    return 0;
+}
+
+extern "C" {
+
+int mcr_abi_version(void) { return MCR_ABI_VERSION; }
+int mcr_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(mcr_run_options);
+        case 1: return (int)sizeof(mcr_result);
+        case 2: return (int)sizeof(mcr_host_request);
+        default: return -1;
+    }
+}
+const char* mcr_last_error(void) { return g_err; }
+
+int mcr_device_count(int* n) {
+    if (!n) return fail("mcr_device_count: null argument");
+    int c = 0;
+    cudaError_t err = cudaGetDeviceCount(&c);
+    if (err != cudaSuccess || c <= 0) {
+        *n = 0;
+        return fail("no usable CUDA device: %s", err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+    }
+    *n = c;
+    return 0;
+}
+
+// ---- host Cholesky / transform (fp64) ------------------------------------------------------------
+int mcr_build_transform(const double* Sigma, int N, int lds, int mode, double* A) {
+    if (!Sigma || !A || N <= 0 || lds < N) return fail("mcr_build_transform: bad arguments");
+    if (mode != MCR_TRANSFORM_LOWER && mode != MCR_TRANSFORM_GSL_FULL) return fail("mcr_build_transform: unknown mode %d", mode);
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) A[(size_t)i * N + j] = Sigma[(size_t)i * lds + j];
+    // left-looking Cholesky on the lower triangle, inner products accumulated left to right
+    for (int j = 0; j < N; ++j) {
+        for (int i = j; i < N; ++i) {
+            double t = 0.0;
+            for (int k = 0; k < j; ++k) t += A[(size_t)j * N + k] * A[(size_t)i * N + k];
+            A[(size_t)i * N + j] -= t;
+        }
+        const double ajj = A[(size_t)j * N + j];
+        if (!(ajj > 0.0) || !std::isfinite(ajj)) return fail("mcr_build_transform: Sigma is not positive definite (pivot %d = %g)", j, ajj);
+        const double inv = 1.0 / std::sqrt(ajj);
+        for (int i = j; i < N; ++i) A[(size_t)i * N + j] *= inv;
+    }
+    for (int i = 0; i < N; ++i)
+        for (int j = i + 1; j < N; ++j)
+            A[(size_t)i * N + j] = (mode == MCR_TRANSFORM_GSL_FULL) ? Sigma[(size_t)j * lds + i] : 0.0;
+    return 0;
+}
+
+// ---- engine --------------------------------------------------------------------------------------
+int mcr_create(int device, mcr_engine** out) {
+    if (!out) return fail("mcr_create: null out");
+    *out = nullptr;
+    int n = 0;
+    if (mcr_device_count(&n) != 0) return -1;
+    if (device < 0 || device >= n) return fail("mcr_create: device %d out of range (have %d)", device, n);
+    ensure_registered();
+    MCR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MCR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail("mcr_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    mcr_engine* e = new mcr_engine();
+    e->device = device;
+    e->num_sms = prop.multiProcessorCount;
+    cudaError_t err = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    ok(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    ok(cudaEventCreate(&e->ev0));
+    ok(cudaEventCreate(&e->ev1));
+    for (int i = 0; i < 2 * MAX_TIMED_CHUNKS; ++i) ok(cudaEventCreate(&e->evk[i]));
+    ok(cudaMalloc(&e->d_flag_list, sizeof(uint32_t) * FLAG_CAP));
+    ok(cudaMalloc(&e->d_flag_count, sizeof(uint32_t)));
+    ok(cudaMalloc(&e->d_accum, sizeof(unsigned long long) * 2));
+    ok(cudaMalloc(&e->d_block_partials, sizeof(uint64_t) * 2 * MAX_GRID));
+    ok(cudaMalloc(&e->d_partials, sizeof(uint64_t) * MCR_PARTIAL_WORDS));
+    ok(cudaMallocHost(&e->h_partials, sizeof(uint64_t) * MCR_PARTIAL_WORDS));
+    if (err != cudaSuccess) {
+        mcr_destroy(e);
+        return fail("mcr_create: allocation failed: %s", cudaGetErrorString(err));
+    }
+    *out = e;
+    return 0;
+}
+
+int mcr_destroy(mcr_engine* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_mu); cudaFree(e->d_Acm);
+    cudaFree(e->d_flag_list); cudaFree(e->d_flag_count); cudaFree(e->d_accum);
+    cudaFree(e->d_block_partials); cudaFree(e->d_partials);
+    if (e->h_partials) cudaFreeHost(e->h_partials);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    for (int i = 0; i < 2 * MAX_TIMED_CHUNKS; ++i) if (e->evk[i]) cudaEventDestroy(e->evk[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return 0;
+}
+
+int mcr_upload_model(mcr_engine* e, int N, const double* mu, const double* A, int a_is_lower) {
+    if (!e || !mu || !A) return fail("mcr_upload_model: null argument");
+    if (N <= 0 || N >= MCR_MAX_HIST) return fail("mcr_upload_model: N=%d out of range [1, %d]", N, MCR_MAX_HIST - 1);
+    if (set_device(e)) return -1;
+    for (int i = 0; i < N; ++i) {
+        if (!std::isfinite(mu[i])) return fail("mcr_upload_model: mu[%d] is not finite", i);
+        for (int j = 0; j < N; ++j) {
+            const double a = A[(size_t)i * N + j];
+            if (!std::isfinite(a)) return fail("mcr_upload_model: A[%d][%d] is not finite", i, j);
+            if (a_is_lower && j > i && a != 0.0) return fail("mcr_upload_model: a_is_lower set but A[%d][%d]=%g", i, j, a);
+        }
+    }
+    MCR_CUDA(cudaStreamSynchronize(e->stream));
+    e->N = N;
+    e->lower = a_is_lower != 0;
+    e->mu.assign(mu, mu + N);
+    e->A.assign(A, A + (size_t)N * N);
+    e->w.assign(N, 1.0 / N);
+    e->packed.assign(registry().n, std::vector<float>());
+    e->gen = g_next_gen.fetch_add(1);
+    // fp64 copies for the exact / fix-up kernel (A column-major)
+    if (N != e->N_alloc) {
+        cudaFree(e->d_mu); cudaFree(e->d_Acm);
+        e->d_mu = nullptr; e->d_Acm = nullptr; e->N_alloc = 0;
+        MCR_CUDA(cudaMalloc(&e->d_mu, sizeof(double) * N));
+        MCR_CUDA(cudaMalloc(&e->d_Acm, sizeof(double) * (size_t)N * N));
+        e->N_alloc = N;
+    }
+    std::vector<double> Acm((size_t)N * N);
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) Acm[(size_t)j * N + i] = A[(size_t)i * N + j];
+    MCR_CUDA(cudaMemcpy(e->d_mu, mu, sizeof(double) * N, cudaMemcpyHostToDevice));
+    MCR_CUDA(cudaMemcpy(e->d_Acm, Acm.data(), sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice));
+    // guard-band ingredient: gamma_i * sum_j |A_ij| with gamma_i = (terms_i + 3) * 2^-24
+    const double u = std::ldexp(1.0, -24);
+    e->gamma_rowabs_max = 0;
+    for (int i = 0; i < N; ++i) {
+        double s = 0;
+        for (int j = 0; j < N; ++j) s += std::fabs(A[(size_t)i * N + j]);
+        const int terms = e->lower ? i + 1 : N;
+        e->gamma_rowabs_max = std::max(e->gamma_rowabs_max, (terms + 3) * u * s);
+    }
+    return 0;
+}
+
+int mcr_set_portfolio_weights(mcr_engine* e, const double* w, int N) {
+    if (!e || !w) return fail("mcr_set_portfolio_weights: null argument");
+    if (N != e->N) return fail("mcr_set_portfolio_weights: N=%d but the uploaded model has N=%d", N, e->N);
+    e->w.assign(w, w + N);
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- launch plumbing -----------------------------------------------------------------------------
+namespace mcr {
+
+static float round_up_to_float(double v) {
+    float f = (float)v;
+    if ((double)f < v) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
+struct RunPlan {
+    int kernel;       // MCR_KERNEL_*
+    int variant;      // FFMA variant index or -1
+    int NT;
+    bool recheck;
+};
+
+static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool normals, RunPlan* plan) {
+    const int want = opt ? opt->kernel : MCR_KERNEL_AUTO;
+    plan->recheck = !(opt && opt->no_recheck);
+    plan->variant = -1;
+    plan->NT = e->N;
+    if (want == MCR_KERNEL_EXACT) { plan->kernel = MCR_KERNEL_EXACT; return 0; }
+    if (want == MCR_KERNEL_TENSOR) return fail("tensor-core kernel is not available in this build for this entry point");
+    const int v = find_variant(e->N, e->lower, normals);
+    if (v >= 0) {
+        plan->kernel = MCR_KERNEL_FFMA; plan->variant = v; plan->NT = registry().v[v].NT;
+        return 0;
+    }
+    if (want == MCR_KERNEL_FFMA)
+        return fail("no FFMA instantiation for N=%d (%s transform); FFMA path covers N <= %d lower / N <= 100 dense",
+                    e->N, e->lower ? "lower" : "dense", MCR_FFMA_MAX_N);
+    plan->kernel = MCR_KERNEL_EXACT;  // AUTO beyond the FFMA range: fp64 kernel (still GPU)
+    return 0;
+}
+
+// enqueue one full run on stream s; partials accumulate into d_out (zeroed here)
+int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, double x, int k,
+                       const mcr_run_options* opt, const double* dZ, uint64_t* d_out, cudaStream_t s) {
+    if (e->N <= 0) return fail("no model uploaded (call mcr_upload_model first)");
+    if (!std::isfinite(x)) return fail("x is not finite");
+    if (set_device(e)) return -1;
+    RunPlan plan;
+    if (make_plan(e, opt, dZ != nullptr, &plan)) return -1;
+    const int N = e->N;
+    const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
+    int32_t* d_S = opt ? opt->d_S_values : nullptr;
+    int launches = 0;
+    e->n_timed = 0;
+
+    MCR_CUDA(cudaMemsetAsync(d_out, 0, sizeof(uint64_t) * MCR_PARTIAL_WORDS, s));
+
+    const FfmaVariant* var = plan.variant >= 0 ? &registry().v[plan.variant] : nullptr;
+    int grid_full = 0;
+    FfmaParams fp{};
+    if (var) {
+        // thresholds c_i = mu_i + x (padded rows can never hit) and the guard band
+        std::vector<float> c(plan.NT, 1.0f);
+        double cabs_gamma_max = 0;
+        const double u = std::ldexp(1.0, -24);
+        for (int i = 0; i < N; ++i) {
+            const double ci = e->mu[i] + x;
+            c[i] = (float)ci;
+            const int terms = e->lower ? i + 1 : N;
+            cabs_gamma_max = std::max(cabs_gamma_max, (terms + 3) * u * std::fabs(ci));
+        }
+        const double safety = 2.0;
+        if (plan.recheck) {
+            fp.delta = round_up_to_float(safety * (cabs_gamma_max + (double)BOX_MULLER_ZMAX * e->gamma_rowabs_max) + 1e-30);
+            fp.delta_rel = round_up_to_float(safety * e->gamma_rowabs_max);
+            fp.delta_abs = round_up_to_float(safety * cabs_gamma_max + 1e-30);
+        } else {
+            fp.delta = 0.f; fp.delta_rel = 0.f; fp.delta_abs = 0.f;
+        }
+        // constant storage: transform (only when this device's copy is stale) and thresholds
+        {
+            std::lock_guard<std::mutex> lk(g_const_mu);
+            ConstState& st = g_const_state[{e->device, var->symbol_tag}];
+            if (st.gen != e->gen || st.variant != plan.variant) {
+                std::vector<float>& packed = e->packed[plan.variant];
+                if (packed.empty()) {
+                    packed.resize(2 * (size_t)var->n_pairs);
+                    var->pack(e->A.data(), N, packed.data());
+                }
+                // a previous launch on another stream may still read the old contents
+                MCR_CUDA(cudaDeviceSynchronize());
+                MCR_CUDA(var->upload_A(packed.data(), s));
+                st.gen = e->gen; st.variant = plan.variant;
+            }
+            if (st.c_gen != e->gen || st.c_variant != plan.variant || st.c_x != x) {
+                // pageable source: the runtime stages it before returning, so `c` may go out of scope
+                MCR_CUDA(var->upload_c(c.data(), s));
+                st.c_gen = e->gen; st.c_variant = plan.variant; st.c_x = x;
+            }
+        }
+        int bps = 0;
+        MCR_CUDA(var->occupancy(128, &bps));
+        if (bps < 1) return fail("FFMA kernel NT=%d cannot be resident", plan.NT);
+        grid_full = std::min(e->num_sms * bps, MAX_GRID);
+        fp.key0 = key0; fp.key1 = key1; fp.k = k; fp.N = N;
+        fp.flag_list = e->d_flag_list; fp.flag_count = e->d_flag_count; fp.flag_cap = FLAG_CAP;
+        fp.block_partials = e->d_block_partials;
+    }
+
+    for (uint64_t done = 0; done < M || (M == 0 && done == 0); done += CHUNK_PATHS) {
+        const uint64_t m = std::min<uint64_t>(CHUNK_PATHS, M - done);
+        if (m == 0) break;
+        MCR_CUDA(cudaMemsetAsync(e->d_accum, 0, sizeof(unsigned long long) * 2, s));
+        MCR_CUDA(cudaMemsetAsync(e->d_flag_count, 0, sizeof(uint32_t), s));
+        FinalizeParams fin{};
+        fin.M = m; fin.out = d_out; fin.accum = e->d_accum;
+        ExactParams xp{};
+        xp.M = m; xp.path_offset = path_offset + done; xp.key0 = key0; xp.key1 = key1;
+        xp.N = N; xp.k = k; xp.lower = e->lower ? 1 : 0; xp.x = x;
+        xp.mu = e->d_mu; xp.A_cm = e->d_Acm;
+        xp.Z = dZ ? dZ + done * (uint64_t)N : nullptr;
+        xp.S_out = d_S ? d_S + done : nullptr;
+        xp.accum = e->d_accum;
+        if (var) {
+            fp.M = m; fp.path_offset = path_offset + done;
+            fp.Z = xp.Z; fp.S_out = xp.S_out;
+            const uint64_t need = (m + 127) / 128;
+            const int grid = (int)std::min<uint64_t>((uint64_t)grid_full, need);
+            const bool timed = e->n_timed < MAX_TIMED_CHUNKS;
+            if (timed) MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed], s));
+            MCR_CUDA(var->launch(fp, grid, 128, s));
+            if (timed) { MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed + 1], s)); ++e->n_timed; }
+            ++launches;
+            if (plan.recheck) {
+                xp.flag_list = e->d_flag_list; xp.flag_count = e->d_flag_count; xp.flag_cap = FLAG_CAP;
+                MCR_CUDA(launch_exact(xp, e->num_sms, s));
+                ++launches;
+            }
+            fin.block_partials = e->d_block_partials; fin.n_blocks = grid;
+            fin.flag_count = e->d_flag_count; fin.flag_cap = FLAG_CAP;
+        } else {
+            const bool timed = e->n_timed < MAX_TIMED_CHUNKS;
+            if (timed) MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed], s));
+            MCR_CUDA(launch_exact(xp, e->num_sms, s));
+            if (timed) { MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed + 1], s)); ++e->n_timed; }
+            ++launches;
+            fin.block_partials = nullptr; fin.n_blocks = 0; fin.flag_count = nullptr;
+        }
+        MCR_CUDA(launch_finalize(fin, s));
+        ++launches;
+    }
+    e->last_kernel = plan.kernel; e->last_NT = plan.NT; e->last_launches = launches;
+    return 0;
+}
+
+void fill_stats(mcr_result* r) {
+    const double M = (double)r->n_paths;
+    if (r->n_paths == 0) { r->P_hat = r->std_error = r->ci_lower = r->ci_upper = 0.0; return; }
+    r->P_hat = (double)r->count / M;
+    r->std_error = std::sqrt(r->P_hat * (1.0 - r->P_hat) / M);
+    const double margin = 1.96 * r->std_error;
+    r->ci_lower = std::fmax(0.0, r->P_hat - margin);
+    r->ci_upper = std::fmin(1.0, r->P_hat + margin);
+}
+
+}  // namespace mcr
+
+extern "C" {
+
+int mcr_last_main_kernel_ms(mcr_engine* e, float* avg_ms, int* n_launches) {
+    if (!e || !avg_ms || !n_launches) return fail("mcr_last_main_kernel_ms: null argument");
+    if (set_device(e)) return -1;
+    double sum = 0;
+    for (int i = 0; i < e->n_timed; ++i) {
+        MCR_CUDA(cudaEventSynchronize(e->evk[2 * i + 1]));
+        float ms = 0;
+        MCR_CUDA(cudaEventElapsedTime(&ms, e->evk[2 * i], e->evk[2 * i + 1]));
+        sum += ms;
+    }
+    *n_launches = e->n_timed;
+    *avg_ms = e->n_timed ? (float)(sum / e->n_timed) : 0.f;
+    return 0;
+}
+
+int mcr_result_from_partials(const uint64_t* h, mcr_result* out) {
+    if (!h || !out) return fail("mcr_result_from_partials: null argument");
+    memset(out, 0, sizeof(*out));
+    out->n_paths = h[0]; out->count = h[1]; out->sum_S = h[2]; out->n_rechecked = h[3];
+    fill_stats(out);
+    if (h[4] != 0) return fail("fix-up list overflowed (more than %u near-threshold trials in one chunk); result incomplete", FLAG_CAP);
+    return 0;
+}
+
+int mcr_run_async(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, double x, int k,
+                  const mcr_run_options* opt, uint64_t* d_partials, void* cuda_stream) {
+    if (!e || !d_partials) return fail("mcr_run_async: null argument");
+    if (opt && (opt->want_hist || opt->want_portfolio)) return fail("mcr_run_async: extension outputs are only available through mcr_run");
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+    return enqueue_run(e, M, path_offset, seed, x, k, opt, nullptr, d_partials, s);
+}
+
+static int finish_sync(mcr_engine* e, mcr_result* out) {
+    MCR_CUDA(cudaEventRecord(e->ev1, e->stream));
+    MCR_CUDA(cudaMemcpyAsync(e->h_partials, e->d_partials, sizeof(uint64_t) * MCR_PARTIAL_WORDS, cudaMemcpyDeviceToHost, e->stream));
+    MCR_CUDA(cudaStreamSynchronize(e->stream));
+    const int rc = mcr_result_from_partials(e->h_partials, out);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    out->device_ms = ms;
+    out->kernel_used = e->last_kernel; out->padded_N = e->last_NT; out->launches = e->last_launches;
+    return rc;
+}
+
+int mcr_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, double x, int k,
+            const mcr_run_options* opt, mcr_result* out) {
+    if (!e || !out) return fail("mcr_run: null argument");
+    if (set_device(e)) return -1;
+    if (opt && (opt->want_hist || opt->want_portfolio)) return fail("mcr_run: extension outputs not built yet");
+    MCR_CUDA(cudaEventRecord(e->ev0, e->stream));
+    if (enqueue_run(e, M, path_offset, seed, x, k, opt, nullptr, e->d_partials, e->stream)) return -1;
+    return finish_sync(e, out);
+}
+
+int mcr_run_with_normals_device(mcr_engine* e, uint64_t M, const double* d_Z, double x, int k,
+                                const mcr_run_options* opt, mcr_result* out) {
+    if (!e || !out || (!d_Z && M)) return fail("mcr_run_with_normals_device: null argument");
+    if (set_device(e)) return -1;
+    MCR_CUDA(cudaEventRecord(e->ev0, e->stream));
+    if (enqueue_run(e, M, 0, 0, x, k, opt, d_Z, e->d_partials, e->stream)) return -1;
+    return finish_sync(e, out);
+}
+
+int mcr_run_with_normals(mcr_engine* e, uint64_t M, const double* Z, double x, int k,
+                         const mcr_run_options* opt, int32_t* S_values_host, mcr_result* out) {
+    if (!e || !out || (!Z && M)) return fail("mcr_run_with_normals: null argument");
+    if (e->N <= 0) return fail("no model uploaded (call mcr_upload_model first)");
+    if (set_device(e)) return -1;
+    double* dZ = nullptr;
+    int32_t* dS = nullptr;
+    const size_t zbytes = sizeof(double) * (size_t)M * e->N;
+    if (M) MCR_CUDA(cudaMalloc(&dZ, zbytes));
+    int rc = -1;
+    do {
+        if (M && cudaMemcpy(dZ, Z, zbytes, cudaMemcpyHostToDevice) != cudaSuccess) { fail("H2D copy of normals failed"); break; }
+        mcr_run_options o{};
+        if (opt) o = *opt;
+        o.struct_size = sizeof(o);
+        if (S_values_host && M) {
+            if (cudaMalloc(&dS, sizeof(int32_t) * M) != cudaSuccess) { fail("S_values allocation failed"); break; }
+            o.d_S_values = dS;
+        }
+        rc = mcr_run_with_normals_device(e, M, dZ, x, k, &o, out);
+        if (rc == 0 && dS && cudaMemcpy(S_values_host, dS, sizeof(int32_t) * M, cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = fail("D2H copy of S_values failed");
+    } while (0);
+    cudaFree(dZ); cudaFree(dS);
+    return rc;
+}
+
+int mcr_dump_normals(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, float* Z_host, uint32_t* U_host) {
+    if (!e) return fail("mcr_dump_normals: null engine");
+    if (e->N <= 0) return fail("no model uploaded (call mcr_upload_model first)");
+    if (set_device(e)) return -1;
+    const int N = e->N, nb = (N + 3) / 4;
+    float* dZ = nullptr; uint32_t* dU = nullptr;
+    if (Z_host) MCR_CUDA(cudaMalloc(&dZ, sizeof(float) * M * N));
+    if (U_host && cudaMalloc(&dU, sizeof(uint32_t) * M * nb * 4) != cudaSuccess) { cudaFree(dZ); return fail("allocation failed"); }
+    int rc = 0;
+    if (launch_dump(M, path_offset, (uint32_t)seed, (uint32_t)(seed >> 32), N, dZ, dU, e->stream) != cudaSuccess ||
+        cudaStreamSynchronize(e->stream) != cudaSuccess)
+        rc = fail("dump kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (!rc && Z_host && cudaMemcpy(Z_host, dZ, sizeof(float) * M * N, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("D2H failed");
+    if (!rc && U_host && cudaMemcpy(U_host, dU, sizeof(uint32_t) * M * nb * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("D2H failed");
+    cudaFree(dZ); cudaFree(dU);
+    return rc;
+}
+
+int mcr_measure_fp32_peak(mcr_engine* e, float ms_target, double* tflops_out) {
+    if (!e || !tflops_out) return fail("mcr_measure_fp32_peak: null argument");
+    if (set_device(e)) return -1;
+    float* sink = nullptr;
+    MCR_CUDA(cudaMalloc(&sink, sizeof(float)));
+    const int grid = e->num_sms * 8;
+    int iters = 2000;
+    float ms = 0;
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e->ev0, e->stream);
+        if (launch_fp32_peak(grid, iters, sink, e->stream) != cudaSuccess) { cudaFree(sink); return fail("fp32 peak kernel launch failed"); }
+        cudaEventRecord(e->ev1, e->stream);
+        if (cudaStreamSynchronize(e->stream) != cudaSuccess) { cudaFree(sink); return fail("fp32 peak kernel failed"); }
+        cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+        const double flops = (double)grid * 256.0 * (double)iters * 8.0 * 16.0 * 4.0;  // 2 lanes x 2 flops per FFMA2
+        if (rep >= 1) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        if (ms < ms_target && rep < 2) iters = (int)std::min(2.0e6, iters * (double)ms_target / std::max(ms, 0.01f));
+    }
+    cudaFree(sink);
+    *tflops_out = best;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+// Engine object behind the opaque mcr_engine handle (internal).
+#pragma once
+#include "../../include/mcr_b200.h"
+#include "mcr_internal.h"
+
+#include <vector>
+
+namespace mcr {
+constexpr uint64_t CHUNK_PATHS = 1ull << 27;   // trials per launch of the path kernel
+constexpr uint32_t FLAG_CAP = 1u << 22;        // fix-up list entries per chunk (3.1 % of a chunk)
+constexpr int MAX_GRID = 148 * 16 * 2;
+constexpr int MAX_TIMED_CHUNKS = 16;
+int fail(const char* fmt, ...);
+}  // namespace mcr
+
+#define MCR_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return mcr::fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+struct mcr_engine {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evk[2 * mcr::MAX_TIMED_CHUNKS] = {};  // (start, stop) around each path-kernel launch of the last run
+    int n_timed = 0;
+    // model
+    int N = 0;
+    int N_alloc = 0;
+    bool lower = false;
+    uint64_t gen = 0;
+    std::vector<double> mu, A, w;
+    std::vector<std::vector<float>> packed;  // per variant index, filled lazily
+    double* d_mu = nullptr;
+    double* d_Acm = nullptr;
+    double gamma_rowabs_max = 0;  // max_i gamma_i * sum_j |A_ij|
+    // scratch
+    uint32_t* d_flag_list = nullptr;
+    uint32_t* d_flag_count = nullptr;
+    unsigned long long* d_accum = nullptr;
+    uint64_t* d_block_partials = nullptr;
+    uint64_t* d_partials = nullptr;
+    uint64_t* h_partials = nullptr;  // pinned
+    // last async run bookkeeping
+    int last_kernel = 0, last_NT = 0, last_launches = 0;
+};
+
+namespace mcr {
+// enqueue one full run (all chunks) on stream s; partial words accumulate into d_out (zeroed first).
+// dZ != nullptr selects normals mode (device, M x N fp64).
+int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, double x, int k,
+                const mcr_run_options* opt, const double* dZ, uint64_t* d_out, cudaStream_t s);
+void fill_stats(mcr_result* r);
+}  // namespace mcr

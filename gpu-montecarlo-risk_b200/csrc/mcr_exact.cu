@@ -1,0 +1,176 @@
+// fp64 exact kernel (also the fix-up kernel), finalize, generator dump and FP32-peak calibration.
+//
+// exact_kernel evaluates trials in fp64 with the reference's summation order
+// (gsl_blas_dgemv row-major NoTrans as used at src/02-C-serial/monte_carlo_serial.c:72-73:
+//  temp = sum_j z_j * A_ij, sequential and unfused;  R_i = (0 + 1*temp) + mu_i;  hit = R_i < -x).
+// It serves (a) as the fix-up for trials the fp32 kernels flagged as too close to the threshold,
+// (b) as MCR_KERNEL_EXACT for whole runs.  One warp per trial: lanes own rows, normals of the
+// trial sit in shared memory, A is read column-major so a warp's loads coalesce.
+#include "mcr_internal.h"
+#include "mcr_rng.cuh"
+#include "../../include/mcr_b200.h"
+
+namespace mcr {
+
+constexpr int EXACT_WARPS = 4;
+
+__global__ void __launch_bounds__(EXACT_WARPS * 32) exact_kernel(const ExactParams p) {
+    extern __shared__ double s_z[];  // EXACT_WARPS x N
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* z = s_z + (size_t)warp * p.N;
+
+    uint64_t n_items = p.M;
+    if (p.flag_list) {
+        const uint32_t c = *p.flag_count;
+        n_items = c < p.flag_cap ? c : p.flag_cap;
+    }
+    const uint64_t total_warps = (uint64_t)gridDim.x * EXACT_WARPS;
+    const double neg_x = -p.x;
+
+    for (uint64_t w = (uint64_t)blockIdx.x * EXACT_WARPS + warp; w < n_items; w += total_warps) {
+        const uint64_t i = p.flag_list ? (uint64_t)p.flag_list[w] : w;
+        if (p.Z) {
+            for (int j = lane; j < p.N; j += 32) z[j] = p.Z[i * (uint64_t)p.N + j];
+        } else {
+            const uint64_t path = p.path_offset + i;
+            for (int b = lane; 4 * b < p.N; b += 32) {
+                float zf[4];
+                normals4((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)b, p.key0, p.key1, zf);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (4 * b + q < p.N) z[4 * b + q] = (double)zf[q];
+            }
+        }
+        __syncwarp();
+        int S = 0;
+        for (int r = lane; r < p.N; r += 32) {
+            double t = 0.0;
+            const int jend = p.lower ? r + 1 : p.N;
+            for (int j = 0; j < jend; ++j)
+                t = __dadd_rn(t, __dmul_rn(z[j], p.A_cm[(size_t)j * p.N + r]));
+            double R = __dadd_rn(0.0, __dmul_rn(1.0, t));
+            R = __dadd_rn(R, p.mu[r]);
+            S += (R < neg_x) ? 1 : 0;
+        }
+        S = __reduce_add_sync(0xffffffffu, S);
+        if (lane == 0) {
+            if (S >= p.k) atomicAdd(&p.accum[0], 1ull);
+            atomicAdd(&p.accum[1], (unsigned long long)S);
+            if (p.S_out) p.S_out[i] = S;
+            if (p.hist) atomicAdd(&p.hist[S], 1ull);
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_exact(const ExactParams& p, int num_sms, cudaStream_t s) {
+    const size_t smem = sizeof(double) * (size_t)EXACT_WARPS * p.N;
+    int grid = num_sms * 8;
+    if (!p.flag_list) {
+        const uint64_t need = (p.M + EXACT_WARPS - 1) / EXACT_WARPS;
+        if (need < (uint64_t)grid) grid = (int)(need ? need : 1);
+    }
+    exact_kernel<<<grid, EXACT_WARPS * 32, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ---- cross-block reduction -------------------------------------------------------------------
+// out[0] += M, out[1] += count, out[2] += sum_S, out[3] += n_rechecked, out[4] |= status
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams p) {
+    __shared__ unsigned long long s_c[8], s_s[8];
+    unsigned long long c = 0, s = 0;
+    for (int b = threadIdx.x; b < p.n_blocks; b += blockDim.x) {
+        c += p.block_partials[2 * (size_t)b];
+        s += p.block_partials[2 * (size_t)b + 1];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        c += __shfl_down_sync(0xffffffffu, c, o);
+        s += __shfl_down_sync(0xffffffffu, s, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5] = c; s_s[threadIdx.x >> 5] = s; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        c = 0; s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { c += s_c[w]; s += s_s[w]; }
+        uint64_t flagged = 0, status = 0;
+        if (p.flag_count) {
+            const uint32_t f = *p.flag_count;
+            flagged = f < p.flag_cap ? f : p.flag_cap;
+            if (f > p.flag_cap) status = 1;  // fix-up list overflow: result incomplete
+        }
+        if (p.accum) { c += p.accum[0]; s += p.accum[1]; }
+        p.out[0] += p.M;
+        p.out[1] += c;
+        p.out[2] += s;
+        p.out[3] += flagged;
+        p.out[4] |= status;
+    }
+}
+
+cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t s) {
+    finalize_kernel<<<1, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ---- generator dump (parity/debug) -----------------------------------------------------------
+__global__ void dump_kernel(uint64_t M, uint64_t path_offset, uint32_t key0, uint32_t key1, int N,
+                            float* dZ, uint32_t* dU) {
+    const int nb = (N + 3) / 4;
+    const uint64_t total = M * (uint64_t)nb;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = t / nb;
+        const uint32_t b = (uint32_t)(t % nb);
+        const uint64_t path = path_offset + i;
+        if (dU) {
+            const u32x4 u = philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), b, 0u, key0, key1);
+            uint32_t* o = dU + (i * nb + b) * 4;
+            o[0] = u.x; o[1] = u.y; o[2] = u.z; o[3] = u.w;
+        }
+        if (dZ) {
+            float z[4];
+            normals4((uint32_t)path, (uint32_t)(path >> 32), b, key0, key1, z);
+            for (int q = 0; q < 4; ++q)
+                if ((int)(4 * b + q) < N) dZ[i * (uint64_t)N + 4 * b + q] = z[q];
+        }
+    }
+}
+
+cudaError_t launch_dump(uint64_t M, uint64_t path_offset, uint32_t key0, uint32_t key1, int N,
+                        float* dZ, uint32_t* dU, cudaStream_t s) {
+    dump_kernel<<<1184, 256, 0, s>>>(M, path_offset, key0, key1, N, dZ, dU);
+    return cudaGetLastError();
+}
+
+// ---- FP32 pipe calibration: packed FMAs only, 16 independent chains per thread ----------------
+__global__ void __launch_bounds__(256) fp32_peak_kernel(int iters, float* sink) {
+    uint64_t a[16];
+    const float seed = 1.0f + 1e-7f * (float)threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const float v = seed + (float)q;
+        a[q] = (uint64_t)__float_as_uint(v) | ((uint64_t)__float_as_uint(v + 0.5f) << 32);
+    }
+    const float m = 0.999999f, c = 1e-6f;
+    const uint64_t mm = (uint64_t)__float_as_uint(m) | ((uint64_t)__float_as_uint(m) << 32);
+    const uint64_t cc = (uint64_t)__float_as_uint(c) | ((uint64_t)__float_as_uint(c) << 32);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[q]) : "l"(mm), "l"(cc));
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc += __uint_as_float((uint32_t)a[q]) + __uint_as_float((uint32_t)(a[q] >> 32));
+    if (acc == 12345.678f) sink[0] = acc;  // keep the chains alive
+}
+
+cudaError_t launch_fp32_peak(int grid, int iters, float* sink, cudaStream_t s) {
+    fp32_peak_kernel<<<grid, 256, 0, s>>>(iters, sink);
+    return cudaGetLastError();
+}
+
+}  // namespace mcr

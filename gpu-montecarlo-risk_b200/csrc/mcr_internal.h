@@ -1,0 +1,89 @@
+// Internal declarations shared by the CUDA translation units of libmcr_b200.so.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mcr {
+
+// ---- parameters of the fused FFMA path kernel (mcr_ffma.cuh) ------------------------------
+struct FfmaParams {
+    uint64_t M;             // paths of this launch (chunk)
+    uint64_t path_offset;   // global index of the chunk's first path (Philox counter)
+    uint32_t key0, key1;    // Philox key = seed
+    int32_t k;              // tail-event threshold on S
+    int32_t N;              // real asset count (<= NT); row length of Z in normals mode
+    float delta;            // Philox mode: guard band on |R_i + x| (0 disables the recheck)
+    float delta_rel;        // normals mode: band = delta_rel * max_j|z_j| + delta_abs
+    float delta_abs;
+    const double* Z;        // normals mode: device, M x N row-major fp64 (chunk-relative)
+    int32_t* S_out;         // optional per-path S (chunk-relative), or nullptr
+    uint32_t* flag_list;    // chunk-relative indices of paths that need the fp64 fix-up
+    uint32_t* flag_count;
+    uint32_t flag_cap;
+    uint64_t* block_partials;  // [gridDim.x][2] = {count, sum_S} of the unflagged paths
+};
+
+// one compiled instantiation of the FFMA kernel
+struct FfmaVariant {
+    int NT;          // padded asset count the code is unrolled for
+    bool lower;      // triangular (skips the strict upper triangle)
+    bool normals;    // normals read from memory instead of generated
+    int n_pairs;     // float2 entries of the packed transform
+    // pack A (N x N fp64 row-major) into this variant's constant layout (host)
+    void (*pack)(const double* A, int N, float* packed /* 2*n_pairs floats */);
+    // copy packed transform / thresholds into the variant's __constant__ storage
+    cudaError_t (*upload_A)(const float* packed, cudaStream_t s);
+    cudaError_t (*upload_c)(const float* c /* NT floats */, cudaStream_t s);
+    cudaError_t (*launch)(const FfmaParams& p, int grid, int block, cudaStream_t s);
+    cudaError_t (*occupancy)(int block, int* blocks_per_sm);
+    const void* symbol_tag;  // identity of the __constant__ storage this variant shares
+};
+
+constexpr int MAX_VARIANTS = 128;
+struct VariantRegistry {
+    FfmaVariant v[MAX_VARIANTS];
+    int n = 0;
+};
+VariantRegistry& registry();
+void register_variant(const FfmaVariant& v);
+
+// instantiation groups (one translation unit each, see mcr_ffma_inst.cu)
+void register_group0(); void register_group1(); void register_group2(); void register_group3();
+void register_group4(); void register_group5(); void register_group6(); void register_group7();
+
+// ---- fp64 exact / fix-up kernel (mcr_exact.cu) ---------------------------------------------
+struct ExactParams {
+    uint64_t M;                 // paths of the chunk (used when flag_list == nullptr: all paths)
+    uint64_t path_offset;
+    uint32_t key0, key1;
+    int32_t N, k;
+    int32_t lower;              // skip the strict upper triangle (exact: those terms are +-0)
+    double x;
+    const double* mu;           // N
+    const double* A_cm;         // N x N column-major fp64: A_cm[j*N + i] = A[i][j]
+    const double* Z;            // normals mode (chunk-relative) or nullptr -> regenerate with Philox
+    const uint32_t* flag_list;  // or nullptr
+    const uint32_t* flag_count;
+    uint32_t flag_cap;
+    int32_t* S_out;
+    unsigned long long* accum;  // [0] += #{S>=k}, [1] += sum S   (integer atomics: order-independent)
+    unsigned long long* hist;   // optional S histogram (N+1 bins) or nullptr
+};
+cudaError_t launch_exact(const ExactParams& p, int num_sms, cudaStream_t s);
+
+struct FinalizeParams {
+    const uint64_t* block_partials;  // [n_blocks][2]
+    int n_blocks;
+    const unsigned long long* accum; // fix-up accumulators [2]
+    const uint32_t* flag_count;
+    uint32_t flag_cap;
+    uint64_t M;
+    uint64_t* out;                   // MCR_PARTIAL_WORDS, accumulated (+=)
+};
+cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t s);
+
+cudaError_t launch_dump(uint64_t M, uint64_t path_offset, uint32_t key0, uint32_t key1, int N,
+                        float* dZ, uint32_t* dU, cudaStream_t s);
+cudaError_t launch_fp32_peak(int grid, int iters, float* sink, cudaStream_t s);
+
+}  // namespace mcr

@@ -1,0 +1,241 @@
+"""GPU parity tests (run on a B200 with -m gpu).  Everything goes through the C ABI.
+
+Bars:
+  1. identical normals  -> S_values / count / sum_S BIT-EXACT vs the fp64 oracle (both the fp32
+     FFMA2 path with its guard band + fp64 fix-up, and the fp64 exact kernel); P_hat, std_error,
+     CI are then the same fp64 expressions -> compared with == (tolerance 0).
+  2. in-register generator: Philox words bit-exact vs the CPU Philox; normals within 2e-5 absolute
+     of the libm Box-Muller (MUFU approximations); the run on generated normals is bit-exact vs the
+     oracle fed the DUMPED normals.
+  3. independent streams (Philox vs MT19937) agree within 3 sigma of the binomial error.
+  4. shard invariance: totals do not depend on how the path range is partitioned.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from mcr_b200 import api
+from mcr_b200.synthetic import synthetic_model
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def real15():
+    g = np.load(GOLD / "pyref_n15.npz")
+    return g["mu"], g["Sigma"]
+
+
+def model(N):
+    if N == 15:
+        mu, Sigma = real15()
+        return mu, Sigma, 0.02, 5
+    m = synthetic_model(N)
+    return m.mu, m.Sigma, m.x, m.k
+
+
+# ---------------------------------------------------------------- generator
+@pytest.mark.parametrize("offset", [0, 12345, (1 << 32) - 7, (3 << 40) + 1])
+def test_philox_words_bit_exact(engine, oracle, offset):
+    mu, Sigma, x, k = model(15)
+    engine.upload_sigma(mu, Sigma)
+    seed = (0xDEADBEEF << 32) | 67
+    _, U = engine.dump_normals(3000, seed, path_offset=offset, normals=False, uniforms=True)
+    np.testing.assert_array_equal(U, oracle.philox_uniforms(seed, offset, 3000, 15))
+
+
+def test_normals_close_to_libm_box_muller_and_standard(engine, oracle):
+    mu, Sigma, x, k = model(50)
+    engine.upload_sigma(mu, Sigma)
+    Z, _ = engine.dump_normals(40000, 67)
+    Zo = oracle.philox_normals(67, 0, 40000, 50)
+    assert np.abs(Z - Zo).max() < 2e-5
+    z = Z.astype(np.float64).ravel()
+    assert abs(z.mean()) < 5 / np.sqrt(z.size)
+    assert abs(z.var() - 1.0) < 5 * np.sqrt(2.0 / z.size)
+    assert abs((z ** 3).mean()) < 0.02 and abs((z ** 4).mean() - 3.0) < 0.05
+    assert np.abs(Z).max() <= 6.8
+    # columns are uncorrelated
+    c = np.corrcoef(Z[:, :8].T)
+    assert np.abs(c - np.eye(8)).max() < 0.03
+
+
+# ---------------------------------------------------------------- identical normals
+@pytest.mark.parametrize("name", ["pyref_n15.npz", "pyref_n25.npz"])
+@pytest.mark.parametrize("kernel", [api.KERNEL_FFMA, api.KERNEL_EXACT])
+def test_golden_python_reference_bit_exact(engine, name, kernel):
+    g = np.load(GOLD / name)
+    engine.upload_sigma(g["mu"], g["Sigma"], api.TRANSFORM_LOWER)
+    r = engine.run_with_normals(g["Z"], float(g["x"]), int(g["k"]), kernel=kernel)
+    np.testing.assert_array_equal(r.S_values, g["S_values"])
+    assert r.count == int(g["count"]) and r.sum_S == int(g["S_values"].sum())
+    assert (r.P_hat, r.std_error, r.ci_lower, r.ci_upper) == \
+        (float(g["P_hat"]), float(g["std_error"]), float(g["ci_lower"]), float(g["ci_upper"]))
+    assert r.kernel == ("ffma" if kernel == api.KERNEL_FFMA else "exact")
+
+
+@pytest.mark.parametrize("N,mode,M", [(15, api.TRANSFORM_GSL_FULL, 200000), (15, api.TRANSFORM_LOWER, 100000),
+                                      (25, api.TRANSFORM_GSL_FULL, 60000), (50, api.TRANSFORM_LOWER, 60000),
+                                      (50, api.TRANSFORM_GSL_FULL, 40000), (100, api.TRANSFORM_LOWER, 30000),
+                                      (100, api.TRANSFORM_GSL_FULL, 20000), (128, api.TRANSFORM_LOWER, 20000)])
+def test_c_serial_stream_bit_exact(engine, oracle, N, mode, M):
+    """Normals drawn exactly like the C-serial model (MT19937 + polar, seed 67), fed to both sides."""
+    mu, Sigma, x, k = model(N)
+    A = engine.upload_sigma(mu, Sigma, mode)
+    np.testing.assert_array_equal(A, oracle.transform(Sigma, mode))
+    ro = oracle.run_mt19937(A, mu, k, x, M, 67, want_Z=True)
+    for kernel in (api.KERNEL_FFMA, api.KERNEL_EXACT):
+        r = engine.run_with_normals(ro["Z"], x, k, kernel=kernel)
+        np.testing.assert_array_equal(r.S_values, ro["S_values"])
+        assert (r.count, r.sum_S, r.n_paths) == (ro["count"], ro["sum_S"], M)
+        assert (r.P_hat, r.std_error, r.ci_lower, r.ci_upper) == oracle.stats(ro["count"], M)
+    assert r.n_rechecked == 0  # exact kernel rechecks nothing
+
+
+def test_real_data_golden_counts(engine, oracle):
+    """Shipped 15-index data, config.yaml x/k/seed, M = 1e6: the counts frozen in SURVEY.md §8c."""
+    mu, Sigma = real15()
+    for mode, want in ((api.TRANSFORM_GSL_FULL, (47605, 674239)), (api.TRANSFORM_LOWER, (47283, 673423))):
+        A = engine.upload_sigma(mu, Sigma, mode)
+        Z = oracle.run_mt19937(A, mu, 5, 0.02, 1000000, 67, want_S=False, want_Z=True)["Z"]
+        r = engine.run_with_normals(Z, 0.02, 5)
+        assert (r.count, r.sum_S) == want
+        assert list(r.S_values[:8]) == [0, 0, 3, 0, 3, 0, 0, 0]
+
+
+def test_guard_band_catches_near_threshold_trials(engine, oracle):
+    """Adversarial normals: trials constructed so that some R_i sits within 1e-9 of -x.  fp32 alone
+    would mis-decide some; the band + fp64 fix-up must still be bit-exact."""
+    mu, Sigma, x, k = model(15)
+    A = engine.upload_sigma(mu, Sigma, api.TRANSFORM_LOWER)
+    rng = np.random.default_rng(5)
+    M = 20000
+    Z = rng.standard_normal((M, 15))
+    # solve for z_0 such that R_0 = mu_0 + A_00 z_0 = -x + eps
+    eps = rng.uniform(-2e-9, 2e-9, size=M)
+    Z[:, 0] = (-x + eps - mu[0]) / A[0, 0]
+    ro = oracle.run_normals(A, mu, k, x, Z)
+    r = engine.run_with_normals(Z, x, k, kernel=api.KERNEL_FFMA)
+    np.testing.assert_array_equal(r.S_values, ro["S_values"])
+    assert r.count == ro["count"] and r.n_rechecked >= M // 2
+    raw = engine.run_with_normals(Z, x, k, kernel=api.KERNEL_FFMA, no_recheck=True)
+    assert raw.n_rechecked == 0
+    assert (raw.S_values != ro["S_values"]).sum() > 0  # fp32 alone does flip decisions here
+
+
+# ---------------------------------------------------------------- in-register generator
+@pytest.mark.parametrize("N,mode,M", [(15, api.TRANSFORM_LOWER, 300000), (15, api.TRANSFORM_GSL_FULL, 100000),
+                                      (25, api.TRANSFORM_LOWER, 100000), (50, api.TRANSFORM_LOWER, 200000),
+                                      (50, api.TRANSFORM_GSL_FULL, 50000), (64, api.TRANSFORM_LOWER, 50000),
+                                      (100, api.TRANSFORM_LOWER, 100000), (128, api.TRANSFORM_LOWER, 30000)])
+def test_philox_run_bit_exact_vs_oracle_on_dumped_normals(engine, oracle, N, mode, M):
+    mu, Sigma, x, k = model(N)
+    A = engine.upload_sigma(mu, Sigma, mode)
+    seed, off = 67, 1000003
+    Z, _ = engine.dump_normals(M, seed, path_offset=off)
+    ro = oracle.run_normals(A, mu, k, x, Z)
+    r = engine.run(M, seed, x, k, path_offset=off)
+    assert r.kernel == "ffma" and r.padded_N >= N
+    assert (r.count, r.sum_S, r.n_paths) == (ro["count"], ro["sum_S"], M)
+    rx = engine.run(M, seed, x, k, path_offset=off, kernel=api.KERNEL_EXACT)
+    assert (rx.count, rx.sum_S) == (ro["count"], ro["sum_S"])
+    h = api.simulate_host(mu, A, M, seed, x, k, a_is_lower=(mode == api.TRANSFORM_LOWER), want_S_values=True)
+    # simulate_host starts at path 0: compare with its own dump
+    Z0, _ = engine.dump_normals(M, seed)
+    r0 = oracle.run_normals(A, mu, k, x, Z0)
+    np.testing.assert_array_equal(h.S_values, r0["S_values"])
+    assert (h.count, h.sum_S) == (r0["count"], r0["sum_S"])
+
+
+def test_independent_streams_agree_within_3_sigma(engine, oracle):
+    for N, mode in ((15, api.TRANSFORM_GSL_FULL), (50, api.TRANSFORM_LOWER)):
+        mu, Sigma, x, k = model(N)
+        A = engine.upload_sigma(mu, Sigma, mode)
+        Mo, Mg = 400000, 20000000
+        ro = oracle.run_mt19937(A, mu, k, x, Mo, 67, want_S=False)
+        r = engine.run(Mg, 67, x, k)
+        po, pg = ro["count"] / Mo, r.P_hat
+        se = np.sqrt(po * (1 - po) / Mo + pg * (1 - pg) / Mg)
+        assert abs(po - pg) <= 3 * se, (N, po, pg, se)
+        mean_S_o, mean_S_g = ro["sum_S"] / Mo, r.sum_S / Mg
+        assert abs(mean_S_o - mean_S_g) < 0.05 * max(mean_S_o, 1e-3) + 3e-3
+
+
+# ---------------------------------------------------------------- sharding / full size properties
+def test_shard_invariance(engine):
+    mu, Sigma, x, k = model(50)
+    engine.upload_sigma(mu, Sigma)
+    M = 3000001
+    whole = engine.run(M, 99, x, k)
+    cuts = [0, 1, 777777, 2000000, M]
+    parts = [engine.run(b - a, 99, x, k, path_offset=a) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert sum(p.count for p in parts) == whole.count
+    assert sum(p.sum_S for p in parts) == whole.sum_S
+    assert sum(p.n_paths for p in parts) == M
+    assert engine.run(M, 100, x, k).sum_S != whole.sum_S  # the seed matters
+
+
+def test_full_size_stoxx50_shape_properties(engine):
+    """BASELINE config 2 at full size (N=50, M=1e8): additivity over shards, determinism,
+    statistics consistent with the counts, chunking (M > one chunk of 2^27 paths)."""
+    mu, Sigma, x, k = model(50)
+    engine.upload_sigma(mu, Sigma)
+    M = 100000000
+    a = engine.run(M, 67, x, k)
+    b = engine.run(M, 67, x, k)
+    assert (a.count, a.sum_S, a.n_rechecked) == (b.count, b.sum_S, b.n_rechecked)
+    half = [engine.run(M // 2, 67, x, k, path_offset=o) for o in (0, M // 2)]
+    assert half[0].count + half[1].count == a.count and half[0].sum_S + half[1].sum_S == a.sum_S
+    assert a.P_hat == a.count / M
+    big = engine.run((1 << 27) + 12345, 67, x, k)  # crosses a chunk boundary
+    parts = [engine.run(1 << 27, 67, x, k), engine.run(12345, 67, x, k, path_offset=1 << 27)]
+    assert big.count == parts[0].count + parts[1].count and big.sum_S == parts[0].sum_S + parts[1].sum_S
+    assert 0 < a.n_rechecked < M // 100
+
+
+# ---------------------------------------------------------------- edge cases and errors
+def test_edge_cases(engine, oracle):
+    mu, Sigma, x, k = model(15)
+    A = engine.upload_sigma(mu, Sigma)
+    assert engine.run(0, 1, x, k).n_paths == 0
+    for M in (1, 31, 127, 128, 129, 1000):
+        Z, _ = engine.dump_normals(M, 5)
+        ro = oracle.run_normals(A, mu, k, x, Z)
+        r = engine.run(M, 5, x, k)
+        assert (r.count, r.sum_S, r.n_paths) == (ro["count"], ro["sum_S"], M)
+    r = engine.run(5000, 5, x, 0)
+    assert r.count == 5000 and r.P_hat == 1.0 and r.ci_upper == 1.0       # S >= 0 always
+    r = engine.run(5000, 5, x, 16)
+    assert r.count == 0 and r.std_error == 0.0 and r.ci_lower == 0.0      # S <= N < k
+    # N = 1 and a huge threshold that every trial crosses
+    engine.upload_model(np.array([0.0]), np.array([[0.01]]), a_is_lower=True)
+    r = engine.run(10000, 3, -1.0, 1)   # R < 1 always
+    assert r.count == 10000 and r.sum_S == 10000
+    r = engine.run(10000, 3, 1.0, 1)    # R < -1 never
+    assert r.count == 0 and r.sum_S == 0
+
+
+def test_large_n_falls_back_to_gpu_exact_kernel(engine, oracle):
+    m = synthetic_model(160)
+    A = engine.upload_sigma(m.mu, m.Sigma)
+    Z, _ = engine.dump_normals(5000, 11)
+    ro = oracle.run_normals(A, m.mu, m.k, m.x, Z)
+    r = engine.run(5000, 11, m.x, m.k)
+    assert r.kernel == "exact" and (r.count, r.sum_S) == (ro["count"], ro["sum_S"])
+    with pytest.raises(api.McrError, match="no FFMA instantiation"):
+        engine.run(5000, 11, m.x, m.k, kernel=api.KERNEL_FFMA)
+
+
+def test_error_behaviour():
+    e = api.Engine(0)
+    with pytest.raises(api.McrError, match="no model uploaded"):
+        e.run(10, 1, 0.02, 1)
+    with pytest.raises(api.McrError, match="not finite"):
+        e.upload_model(np.array([np.nan, 0.0]), np.eye(2))
+    with pytest.raises(api.McrError, match="a_is_lower"):
+        e.upload_model(np.zeros(2), np.array([[1.0, 0.5], [0.0, 1.0]]), a_is_lower=True)
+    with pytest.raises(api.McrError, match="out of range"):
+        api.Engine(99)
+    e.close()
