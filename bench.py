@@ -231,7 +231,9 @@ def main():
     eng = api.Engine(local)
     A = eng.upload_sigma(model.mu, model.Sigma, api.TRANSFORM_LOWER)
     partials = torch.zeros(api.MCR_PARTIAL_WORDS, dtype=torch.int64, device="cuda")
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) torch stream: the library launches on it, torch events time it, NCCL uses it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
 
     def step():
         eng.run_async(M, SEED, model.x, model.k, partials.data_ptr(), stream.cuda_stream, path_offset=rank * M)

@@ -23,24 +23,55 @@
 // kernel (mcr_exact.cu) re-evaluates it in the reference's summation order.  The union is
 // bit-identical to evaluating every trial in fp64 on the same normals.
 #pragma once
+#ifndef MCR_PREFETCH_LINES
+#define MCR_PREFETCH_LINES 0
+#endif
+#ifndef MCR_PIPE_DEPTH
+#define MCR_PIPE_DEPTH 8
+#endif
+#ifndef MCR_ABLATE
+#define MCR_ABLATE 0
+#endif
+#ifndef MCR_MIN_BLOCKS
+#define MCR_MIN_BLOCKS 1
+#endif
 #include "mcr_internal.h"
 #include "mcr_rng.cuh"
 
+#include <type_traits>
+#include <utility>
+
 namespace mcr {
+
+// Compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N-1>{}).
+// Used instead of `#pragma unroll` for the big loops: their bodies are so large that nvvm's pragma
+// unroll budget refuses to unroll them at NT >= 128, which turns the accumulators into local memory.
+template <int... I, class F>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, I...>, F&& f) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    static_for_impl(std::make_integer_sequence<int, N>{}, static_cast<F&&>(f));
+}
 
 // per-translation-unit constant storage (each instantiation group has its own copy)
 constexpr int CONST_PAIRS = 5120;            // 40 KB: NT=100 dense (5000) / NT=128 lower (4160)
-static __constant__ float2 cA2[CONST_PAIRS]; // packed transform, column-major row pairs
-static __constant__ float2 cC2[MCR_FFMA_MAX_N_INTERNAL / 2];  // c_i = mu_i + x (row pairs)
+static __constant__ __align__(16) float2 cA2[CONST_PAIRS + 2]; // packed transform, column-major row pairs
+static __constant__ __align__(16) float2 cC2[MCR_FFMA_MAX_N_INTERNAL / 2 + 2];  // c_i = mu_i + x (row pairs)
 
 template <int NT, bool LOWER>
 struct Layout {
     static constexpr int H = NT / 2;  // row pairs
     __host__ __device__ static constexpr int m0(int j) { return LOWER ? j / 2 : 0; }
+    // pairs stored before column j; every column starts on a 16-byte boundary (even pair index).
+    // Closed form (no loop) so that it folds to an immediate at every unrolled use.
+    __host__ __device__ static constexpr int up2(int v) { return (v + 1) & ~1; }
+    __host__ __device__ static constexpr int g(int q) {  // sum_{u<q} up2(H - u)
+        return q * H - q * (q - 1) / 2 + ((H % 2 == 0) ? q / 2 : (q + 1) / 2);
+    }
     __host__ __device__ static constexpr int col_off(int j) {
-        int s = 0;
-        for (int t = 0; t < j; ++t) s += H - m0(t);
-        return s;
+        return LOWER ? 2 * g(j / 2) + ((j & 1) ? up2(H - j / 2) : 0) : j * up2(H);
     }
     static constexpr int n_pairs = col_off(NT);
     static_assert(NT % 2 == 0, "NT must be even");
@@ -52,75 +83,160 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+// same, but pinned in program order relative to the (volatile) transform loads: this is what keeps
+// the software-pipelined load -> use distance intact through nvvm's scheduler
+__device__ __forceinline__ uint64_t ffma2_ordered(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// 16 bytes (two row pairs) from constant memory; asm volatile so the load stays where it is written
+__device__ __forceinline__ void ldc128(uint64_t const_addr, uint64_t& a, uint64_t& b) {
+    asm volatile("ld.const.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(const_addr));
+}
+// prefetch the line holding a (generic) constant-memory address into the uniform/constant cache
+__device__ __forceinline__ void prefetch_const(const void* generic_ptr) {
+    asm volatile("prefetchu.L1 [%0];" :: "l"(generic_ptr));
+}
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
     return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
 }
 
-template <int NT, bool LOWER, bool FROM_NORMALS>
-__global__ void __launch_bounds__(128) ffma_path_kernel(const FfmaParams p) {
+template <int NT, bool LOWER, bool FROM_NORMALS, int PPT>
+__global__ void __launch_bounds__(128, MCR_MIN_BLOCKS) ffma_path_kernel(const FfmaParams p) {
     using L = Layout<NT, LOWER>;
     constexpr int H = L::H;
     constexpr int NB = (NT + 3) / 4;  // Philox blocks per path
+    constexpr int DEPTH = MCR_PIPE_DEPTH;  // 16-byte transform loads in flight ahead of their use
+    constexpr int PREFETCH_LINES = MCR_PREFETCH_LINES;  // 64-byte constant-cache lines touched ahead
 
     uint32_t cnt = 0, sum_s = 0;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t* cA = reinterpret_cast<const uint64_t*>(cA2);
-    const uint64_t* cC = reinterpret_cast<const uint64_t*>(cC2);
+    const uint64_t T = (uint64_t)gridDim.x * blockDim.x;
+    // .const-space byte addresses (ld.const takes those, not generic pointers)
+    const uint64_t cA_const = (uint64_t)__cvta_generic_to_constant(cA2);
+    const uint64_t cC_const = (uint64_t)__cvta_generic_to_constant(cC2);
 
+    // One thread carries PPT trials at a time (trial indices i0, i0 + T, ...): every 16-byte uniform
+    // load of the transform then feeds 2 * PPT packed FMAs instead of 2.  The uniform constant-load
+    // path (LDCU) sustains only about one 16-byte load per 10 cycles per SM sub-partition
+    // (measured), so at PPT = 1 it, not the FMA pipe, bounds the kernel.
 #pragma unroll 1
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.M; i += stride) {
-        const uint64_t path = p.path_offset + i;
-        const uint32_t path_lo = (uint32_t)path, path_hi = (uint32_t)(path >> 32);
-
-        uint64_t acc[H];
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.M; i0 += T * PPT) {
+        uint64_t idx[PPT];
+        bool valid[PPT];
+        uint32_t path_lo[PPT], path_hi[PPT];
 #pragma unroll
-        for (int m = 0; m < H; ++m) acc[m] = cC[m];
-
-        float zmax = 0.0f;
-        const double* zrow = FROM_NORMALS ? p.Z + i * (uint64_t)p.N : nullptr;
-
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            float z[4];
-            if constexpr (FROM_NORMALS) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int j = 4 * b + q;
-                    z[q] = (j < p.N) ? __double2float_rn(zrow[j]) : 0.0f;
-                    zmax = fmaxf(zmax, fabsf(z[q]));
-                }
-            } else {
-                normals4(path_lo, path_hi, (uint32_t)b, p.key0, p.key1, z);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int j = 4 * b + q;
-                if (j < NT) {
-                    const uint64_t zz = pack2(z[q], z[q]);
-#pragma unroll
-                    for (int m = L::m0(j); m < H; ++m)
-                        acc[m] = ffma2(cA[L::col_off(j) + m - L::m0(j)], zz, acc[m]);
-                }
-            }
+        for (int pp = 0; pp < PPT; ++pp) {
+            idx[pp] = i0 + (uint64_t)pp * T;
+            valid[pp] = idx[pp] < p.M;
+            const uint64_t path = p.path_offset + idx[pp];
+            path_lo[pp] = (uint32_t)path;
+            path_hi[pp] = (uint32_t)(path >> 32);
         }
+
+        // acc_i starts at c_i = mu_i + x.  All constant loads are volatile asm on purpose: plain
+        // constant loads are loop-invariant, so nvvm hoists every one of them out of the trial loop
+        // (hundreds of live values) and ptxas has to rematerialise them anyway.
+        uint64_t acc[PPT][H + 1];
+#pragma unroll
+        for (int m = 0; m < H; m += 2) {
+            uint64_t c0, c1;
+            ldc128(cC_const + 8 * m, c0, c1);
+#pragma unroll
+            for (int pp = 0; pp < PPT; ++pp) { acc[pp][m] = c0; acc[pp][m + 1] = c1; }
+        }
+
+        // pipeline prologue: the first DEPTH couples of the transform stream
+        uint64_t pipe[DEPTH][2];
+#pragma unroll
+        for (int e = 0; e < DEPTH; ++e) ldc128(cA_const + 16 * (e < L::n_pairs / 2 ? e : 0), pipe[e][0], pipe[e][1]);
+
+        float zmax[PPT];
+#pragma unroll
+        for (int pp = 0; pp < PPT; ++pp) zmax[pp] = 0.0f;
+
+        static_for<NB>([&](auto b_c) {
+            constexpr int b = decltype(b_c)::value;
+            float z[PPT][4];
+#pragma unroll
+            for (int pp = 0; pp < PPT; ++pp) {
+                if constexpr (FROM_NORMALS) {
+                    const double* zrow = p.Z + (valid[pp] ? idx[pp] : i0) * (uint64_t)p.N;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = 4 * b + q;
+                        z[pp][q] = (j < p.N) ? __double2float_rn(zrow[j]) : 0.0f;
+                        zmax[pp] = fmaxf(zmax[pp], fabsf(z[pp][q]));
+                    }
+                } else {
+#if MCR_ABLATE == 1   // tuning only: no RNG, normals replaced by a 2-instruction hash
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        z[pp][q] = __uint_as_float(0x3f800000u | ((path_lo[pp] * 2654435761u + (uint32_t)(4 * b + q) * 40503u) >> 9)) - 1.5f;
+#else
+                    normals4(path_lo[pp], path_hi[pp], (uint32_t)b, p.key0, p.key1, z[pp]);
+#endif
+                }
+            }
+            static_for<4>([&](auto q_c) {
+                constexpr int q = decltype(q_c)::value;
+                constexpr int j = 4 * b + q;
+                if constexpr (j < NT) {
+                    uint64_t zz[PPT];
+#pragma unroll
+                    for (int pp = 0; pp < PPT; ++pp) zz[pp] = pack2(z[pp][q], z[pp][q]);
+#if MCR_ABLATE == 2   // tuning only: no correlate, one packed FMA per normal keeps the RNG alive
+#pragma unroll
+                    for (int pp = 0; pp < PPT; ++pp) acc[pp][j % H] = ffma2(acc[pp][(j + 1) % H], zz[pp], acc[pp][j % H]);
+#else
+                    constexpr int M0 = L::m0(j);
+                    static_for<(H - M0 + 1) / 2>([&](auto t_c) {
+                        constexpr int m = M0 + 2 * decltype(t_c)::value;
+                        // couple e = rows (2m..2m+3) of column j; the stream of couples is consumed in
+                        // storage order through a DEPTH-deep software pipeline of uniform registers
+                        constexpr int e = (L::col_off(j) + m - M0) / 2;
+                        const uint64_t a0 = pipe[e % DEPTH][0], a1 = pipe[e % DEPTH][1];
+#pragma unroll
+                        for (int pp = 0; pp < PPT; ++pp) {
+                            acc[pp][m] = ffma2_ordered(a0, zz[pp], acc[pp][m]);
+                            if constexpr (m + 1 < H) acc[pp][m + 1] = ffma2_ordered(a1, zz[pp], acc[pp][m + 1]);
+                        }
+                        if constexpr (e + DEPTH < L::n_pairs / 2)
+                            ldc128(cA_const + 16 * (e + DEPTH), pipe[e % DEPTH][0], pipe[e % DEPTH][1]);
+                        // The SM's first-level constant cache is far smaller than the transform (5 KB at
+                        // N = 50), so the stream misses to the GPC-level constant cache once per line and
+                        // the (loosely lock-stepped) warps of the SM all wait on that miss.  Optionally touch
+                        // the line PREFETCH_LINES ahead once per 64-byte line.
+                        if constexpr (PREFETCH_LINES > 0 && e % 4 == 0 && 16 * e + 64 * PREFETCH_LINES < 8 * L::n_pairs)
+                            prefetch_const(reinterpret_cast<const char*>(cA2) + 16 * e + 64 * PREFETCH_LINES);
+                    });
+#endif
+                }
+            });
+        });
 
         // threshold + guard band
-        uint32_t S = 0;
-        float band = 3.0e38f;
 #pragma unroll
-        for (int m = 0; m < H; ++m) {
-            const uint32_t lo = (uint32_t)acc[m], hi = (uint32_t)(acc[m] >> 32);
-            S += (lo >> 31) + (hi >> 31);
-            band = fminf(band, fminf(fabsf(__uint_as_float(lo)), fabsf(__uint_as_float(hi))));
-        }
-        const float delta = FROM_NORMALS ? __fmaf_rn(p.delta_rel, zmax, p.delta_abs) : p.delta;
-        if (band < delta) {
-            const uint32_t slot = atomicAdd(p.flag_count, 1u);
-            if (slot < p.flag_cap) p.flag_list[slot] = (uint32_t)i;
-        } else {
-            cnt += (S >= (uint32_t)p.k) ? 1u : 0u;
-            sum_s += S;
-            if (p.S_out) p.S_out[i] = (int32_t)S;
+        for (int pp = 0; pp < PPT; ++pp) {
+            uint32_t S = 0;
+            float band = 3.0e38f;
+#pragma unroll
+            for (int m = 0; m < H; ++m) {
+                const uint32_t lo = (uint32_t)acc[pp][m], hi = (uint32_t)(acc[pp][m] >> 32);
+                S += (lo >> 31) + (hi >> 31);
+                band = fminf(band, fminf(fabsf(__uint_as_float(lo)), fabsf(__uint_as_float(hi))));
+            }
+            const float delta = FROM_NORMALS ? __fmaf_rn(p.delta_rel, zmax[pp], p.delta_abs) : p.delta;
+            if (valid[pp]) {
+                if (band < delta) {
+                    const uint32_t slot = atomicAdd(p.flag_count, 1u);
+                    if (slot < p.flag_cap) p.flag_list[slot] = (uint32_t)idx[pp];
+                } else {
+                    cnt += (S >= (uint32_t)p.k) ? 1u : 0u;
+                    sum_s += S;
+                    if (p.S_out) p.S_out[idx[pp]] = (int32_t)S;
+                }
+            }
         }
     }
 
@@ -143,6 +259,7 @@ __global__ void __launch_bounds__(128) ffma_path_kernel(const FfmaParams p) {
 template <int NT, bool LOWER>
 void pack_transform(const double* A, int N, float* packed) {
     using L = Layout<NT, LOWER>;
+    for (int t = 0; t < 2 * L::n_pairs; ++t) packed[t] = 0.0f;
     for (int j = 0; j < NT; ++j)
         for (int m = L::m0(j); m < L::H; ++m) {
             const int idx = L::col_off(j) + m - L::m0(j);
@@ -162,20 +279,20 @@ static cudaError_t upload_c_impl(const float* c, int NT, cudaStream_t s) {
     return cudaMemcpyToSymbolAsync(cC2, c, sizeof(float) * (size_t)NT, 0, cudaMemcpyHostToDevice, s);
 }
 
-template <int NT, bool LOWER, bool FROM_NORMALS>
+template <int NT, bool LOWER, bool FROM_NORMALS, int PPT>
 FfmaVariant make_variant() {
     FfmaVariant v{};
-    v.NT = NT; v.lower = LOWER; v.normals = FROM_NORMALS;
+    v.NT = NT; v.lower = LOWER; v.normals = FROM_NORMALS; v.ppt = PPT;
     v.n_pairs = Layout<NT, LOWER>::n_pairs;
     v.pack = &pack_transform<NT, LOWER>;
     v.upload_A = [](const float* packed, cudaStream_t s) { return upload_A_impl(packed, Layout<NT, LOWER>::n_pairs, s); };
     v.upload_c = [](const float* c, cudaStream_t s) { return upload_c_impl(c, NT, s); };
     v.launch = [](const FfmaParams& p, int grid, int block, cudaStream_t s) {
-        ffma_path_kernel<NT, LOWER, FROM_NORMALS><<<grid, block, 0, s>>>(p);
+        ffma_path_kernel<NT, LOWER, FROM_NORMALS, PPT><<<grid, block, 0, s>>>(p);
         return cudaGetLastError();
     };
     v.occupancy = [](int block, int* bps) {
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, ffma_path_kernel<NT, LOWER, FROM_NORMALS>, block, 0);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, ffma_path_kernel<NT, LOWER, FROM_NORMALS, PPT>, block, 0);
     };
     v.symbol_tag = (const void*)&cA2;
     return v;

@@ -2,6 +2,12 @@
 // (-DMCR_INST_GROUP=g) so the fully unrolled kernels build in parallel; each group owns its
 // own copy of the __constant__ transform storage.
 #define MCR_FFMA_MAX_N_INTERNAL 128
+#ifndef MCR_PPT2_MAX_NT
+#define MCR_PPT2_MAX_NT 0
+#endif
+#ifndef MCR_DEV_PPT
+#define MCR_DEV_PPT 2
+#endif
 #include "mcr_ffma.cuh"
 
 #ifndef MCR_INST_GROUP
@@ -10,13 +16,16 @@
 
 namespace mcr {
 
+// trials per thread: 2 while both accumulator sets fit the register file without spilling
+template <int NT> constexpr int ppt_for() { return NT <= MCR_PPT2_MAX_NT ? 2 : 1; }
+
 template <int NT, bool DENSE_TOO>
 static void reg_size() {
-    register_variant(make_variant<NT, true, false>());
-    register_variant(make_variant<NT, true, true>());
+    register_variant(make_variant<NT, true, false, ppt_for<NT>()>());
+    register_variant(make_variant<NT, true, true, 1>());
     if constexpr (DENSE_TOO) {
-        register_variant(make_variant<NT, false, false>());
-        register_variant(make_variant<NT, false, true>());
+        register_variant(make_variant<NT, false, false, ppt_for<NT>()>());
+        register_variant(make_variant<NT, false, true, 1>());
     }
 }
 
@@ -24,7 +33,12 @@ static void reg_size() {
 #define MCR_GROUP_FN(g) MCR_GROUP_FN_(g)
 
 void MCR_GROUP_FN(MCR_INST_GROUP)() {
-#if MCR_INST_GROUP == 0
+#if defined(MCR_DEV_SINGLE)
+    // development build: one size only (fast rebuilds for kernel tuning)
+#if MCR_INST_GROUP == 1
+    register_variant(make_variant<MCR_DEV_SINGLE, true, false, MCR_DEV_PPT>());
+#endif
+#elif MCR_INST_GROUP == 0
     reg_size<8, true>(); reg_size<16, true>(); reg_size<24, true>(); reg_size<32, true>();
 #elif MCR_INST_GROUP == 1
     reg_size<40, true>(); reg_size<48, false>(); reg_size<50, true>();

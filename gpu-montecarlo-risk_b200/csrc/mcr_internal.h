@@ -28,6 +28,7 @@ struct FfmaVariant {
     int NT;          // padded asset count the code is unrolled for
     bool lower;      // triangular (skips the strict upper triangle)
     bool normals;    // normals read from memory instead of generated
+    int ppt;         // trials carried per thread (transform loads amortised over them)
     int n_pairs;     // float2 entries of the packed transform
     // pack A (N x N fp64 row-major) into this variant's constant layout (host)
     void (*pack)(const double* A, int N, float* packed /* 2*n_pairs floats */);

@@ -1,10 +1,11 @@
 """ctypes binding of libmcr_b200.so (include/mcr_b200.h).  No fallback: if the shared
 library has not been built, importing the binding raises."""
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG_ROOT = Path(__file__).resolve().parent.parent
-LIB_PATH = PKG_ROOT / "libmcr_b200.so"
+LIB_PATH = Path(os.environ.get("MCR_B200_LIB", PKG_ROOT / "libmcr_b200.so"))  # override: kernel-tuning builds
 
 MCR_MAX_HIST = 1025
 MCR_PORTFOLIO_BINS = 2048
