@@ -302,14 +302,28 @@ def main():
         nominal_tf = 148 * 128 * 2 * (clocks.max_mhz or 1965) * 1e6 / 1e12
         sims_per_launch = min(M, 1 << 27)
         achieved_tf = sims_per_launch * flops_per_sim(N) / (k_ms * 1e-3) / 1e12
+        tensor = None
+        if one.kernel == "tensor":
+            # what the tensor pipe actually executes: 3 passes (fp16 hi/lo split) over the padded dense tile
+            kpad = 64 * ((N + 1 + 63) // 64)
+            exec_tf = sims_per_launch * 3 * 2 * one.padded_N * kpad / (k_ms * 1e-3) / 1e12
+            mp = ROOT / "MEASURED_PEAKS.json"
+            bf16_peak = json.load(open(mp)).get("bf16_tflops") if mp.exists() else 1590.0
+            tensor = {"executed_tflops": exec_tf, "peak": bf16_peak, "frac": exec_tf / bf16_peak,
+                      "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, of measured)" if mp.exists() else "fallback 1.59 PFLOP/s (of fallback)",
+                      "note": "the correlate runs on tcgen05 (fp16x3, fp32 accumulate in TMEM); the kernel is bound by the Philox/Box-Muller "
+                              "instruction stream, not by the tensor pipe"}
+        kname = (f"tc_path_kernel<NOUT={one.padded_N}> (tcgen05 fp16x3 correlate)" if one.kernel == "tensor"
+                 else f"ffma_path_kernel<NT={one.padded_N},LOWER,philox>")
         roof = {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
-                "kernel": f"ffma_path_kernel<NT={one.padded_N},LOWER,philox>", "kernel_ms_per_launch": k_ms,
+                "kernel": kname, "kernel_ms_per_launch": k_ms,
                 "launches_timed_per_step": launches_per_kernel_step,
                 "flops_per_sim": flops_per_sim(N),
                 "peak_source": "measured here: FFMA2-only kernel (mcr_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
-                "frac_of_nominal": achieved_tf / nominal_tf, "nominal_peak": nominal_tf,
-                "note": "compute-bound by design: no per-trial HBM traffic (normals and returns live in registers)"}
+                "frac_of_nominal": achieved_tf / nominal_tf, "nominal_peak": nominal_tf, "tensor": tensor,
+                "note": "algorithmic flops F(N)=N^2+3N per simulation over the path kernel's CUDA-event time, against the FP32 FFMA peak "
+                        "(the metric BASELINE.json names); no per-trial HBM traffic (normals and returns never leave the SM)"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cpu = cpu_reference_leg(model)
@@ -320,11 +334,11 @@ def main():
         line = {
             "metric": "simulations/sec", "value": value, "unit": "simulations/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if (launches_per_step and one.kernel == "ffma") else "f16x3+f32acc", "data": "synthetic",
             "config": {"workload": f"Stoxx50-shape synthetic SPD (BASELINE config 2), N={N}, M={M} trials per GPU per step, "
-                                   f"x={model.x}, k={model.k}, seed {SEED}, lower-triangular transform, fp32 FFMA2 correlate + fp64 recheck band",
+                                   f"x={model.x}, k={model.k}, seed {SEED}, lower-triangular transform, kernel={one.kernel if rank == 0 else '?'} + fp64 recheck band",
                        "parallelism": f"paths sharded x{world}, one 64-byte NCCL all-reduce per step" if world > 1 else "single GPU",
-                       "l2": "no HBM/L2-resident inputs: normals are generated in registers, the transform (5.2 KB) is in constant memory"},
+                       "l2": "no HBM/L2-resident inputs to flush: normals are generated in registers, the transform (a few KB) sits in shared/constant memory"},
             "clocks": clocks.summary(),
             "e2e": e2e, "gpu_launches": (launches_per_step or 0) * args.steps,
             "roofline": roof, "cpu_baseline": cpu,

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -167,7 +168,7 @@ int mcr_destroy(mcr_engine* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->d_mu); cudaFree(e->d_Acm);
+    cudaFree(e->d_mu); cudaFree(e->d_Acm); cudaFree(e->d_tc_image);
     cudaFree(e->d_flag_list); cudaFree(e->d_flag_count); cudaFree(e->d_accum);
     cudaFree(e->d_block_partials); cudaFree(e->d_partials);
     if (e->h_partials) cudaFreeHost(e->h_partials);
@@ -249,14 +250,33 @@ struct RunPlan {
     bool recheck;
 };
 
+static int auto_tc_min_n() {
+    static const int v = [] { const char* e = getenv("MCR_AUTO_TC_MIN_N"); return e && *e ? atoi(e) : 36; }();
+    return v;
+}
+
 static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool normals, RunPlan* plan) {
     const int want = opt ? opt->kernel : MCR_KERNEL_AUTO;
     plan->recheck = !(opt && opt->no_recheck);
     plan->variant = -1;
     plan->NT = e->N;
     if (want == MCR_KERNEL_EXACT) { plan->kernel = MCR_KERNEL_EXACT; return 0; }
-    if (want == MCR_KERNEL_TENSOR) return fail("tensor-core kernel is not available in this build for this entry point");
+    const bool tc_ok = !normals && tc_supported(e->N);
+    if (want == MCR_KERNEL_TENSOR) {
+        if (normals) return fail("the tensor-core kernel generates its normals in-kernel; use the FFMA or EXACT kernel with supplied normals");
+        if (!tc_ok) return fail("tensor-core kernel covers N <= %d in this build (N=%d)", tc_max_n(), e->N);
+        plan->kernel = MCR_KERNEL_TENSOR; plan->NT = tc_padded_n(e->N);
+        return 0;
+    }
     const int v = find_variant(e->N, e->lower, normals);
+    // AUTO: the FFMA kernel while the transform (roughly) fits the SM's first-level constant cache, the
+    // tensor-core kernel above that (the FFMA kernel then stalls on constant-cache misses).  Measured
+    // crossover on B200: N = 32 FFMA 2.3e10 vs tensor 2.1e10 sims/s, N = 40 1.6e10 vs 1.7e10
+    // (profiles/r01_sweep_ffma_vs_tensor.log)
+    if (want == MCR_KERNEL_AUTO && tc_ok && (e->N >= auto_tc_min_n() || v < 0)) {
+        plan->kernel = MCR_KERNEL_TENSOR; plan->NT = tc_padded_n(e->N);
+        return 0;
+    }
     if (v >= 0) {
         plan->kernel = MCR_KERNEL_FFMA; plan->variant = v; plan->NT = registry().v[v].NT;
         return 0;
@@ -264,7 +284,7 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
     if (want == MCR_KERNEL_FFMA)
         return fail("no FFMA instantiation for N=%d (%s transform); FFMA path covers N <= %d lower / N <= 100 dense",
                     e->N, e->lower ? "lower" : "dense", MCR_FFMA_MAX_N);
-    plan->kernel = MCR_KERNEL_EXACT;  // AUTO beyond the FFMA range: fp64 kernel (still GPU)
+    plan->kernel = MCR_KERNEL_EXACT;  // AUTO beyond the fast kernels' range: fp64 kernel (still GPU)
     return 0;
 }
 
@@ -336,6 +356,52 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         fp.block_partials = e->d_block_partials;
     }
 
+    TcLaunch tl{};
+    int tc_grid_full = 0;
+    if (plan.kernel == MCR_KERNEL_TENSOR) {
+        // split, swizzled transform image (depends on x through the constant column): rebuilt only when
+        // the model or x changed
+        const size_t bytes = tc_image_bytes(N);
+        if (e->tc_image_cap < bytes) {
+            cudaFree(e->d_tc_image); e->d_tc_image = nullptr; e->tc_image_cap = 0;
+            MCR_CUDA(cudaMalloc(&e->d_tc_image, bytes));
+            e->tc_image_cap = bytes; e->tc_gen = 0;
+        }
+        std::vector<double> c(N);
+        double cabs_max = 0, rowabs_max = 0;
+        for (int i = 0; i < N; ++i) {
+            c[i] = e->mu[i] + x;
+            cabs_max = std::max(cabs_max, std::fabs(c[i]));
+            double srow = 0;
+            for (int j = 0; j < N; ++j) srow += std::fabs(e->A[(size_t)i * N + j]);
+            rowabs_max = std::max(rowabs_max, srow);
+        }
+        if (e->tc_gen != e->gen || e->tc_x != x) {
+            e->tc_host_image.resize(bytes);
+            tc_build(N, e->A.data(), c.data(), e->tc_host_image.data());
+            MCR_CUDA(cudaStreamSynchronize(s));   // a previous run may still read the old image
+            MCR_CUDA(cudaMemcpyAsync(e->d_tc_image, e->tc_host_image.data(), bytes, cudaMemcpyHostToDevice, s));
+            e->tc_gen = e->gen; e->tc_x = x;
+        }
+        // fp16x3: each operand is hi + lo with relative residual 2^-22 (plus fp16-subnormal rounding of tiny
+        // z_lo, absolute 2^-25 per normal), the lo*lo product is dropped, and the tensor core accumulates in
+        // fp32 over 12*KB MMA instructions: budget 2^-19 relative to |c| + sum_j |a_ij||z_j| (3 * 2^-22 for the
+        // split, the rest for accumulation), doubled like the FFMA band.  Calibration on 4M trials per size:
+        // counts are still exact with the band at 1/64 of this (profiles/r01_tc_band_calibrate.log).
+        static const double band_scale = [] { const char* v = getenv("MCR_TC_BAND_SCALE"); return v && *v ? atof(v) : 1.0; }();
+        const double gamma = std::ldexp(1.0, -19);
+        tl.delta_rel = plan.recheck ? round_up_to_float(band_scale * 2.0 * gamma * rowabs_max) : 0.f;
+        tl.delta_abs = plan.recheck ? round_up_to_float(band_scale * 2.0 * gamma * cabs_max + 1e-30) : 0.f;
+        int bps = 0;
+        MCR_CUDA(tc_occupancy(N, &bps));
+        if (bps < 1) return fail("tensor-core kernel for N=%d cannot be resident", N);
+        if (const char* ov = getenv("MCR_TC_CTAS_PER_SM")) { if (atoi(ov) > 0) bps = atoi(ov); }  // tuning override
+        tc_grid_full = std::min(e->num_sms * bps, MAX_GRID);
+        tl.key0 = key0; tl.key1 = key1; tl.k = k; tl.d_image = e->d_tc_image;
+        tl.flag_list = e->d_flag_list; tl.flag_count = e->d_flag_count; tl.flag_cap = FLAG_CAP;
+        tl.block_partials = e->d_block_partials;
+    }
+
     for (uint64_t done = 0; done < M || (M == 0 && done == 0); done += CHUNK_PATHS) {
         const uint64_t m = std::min<uint64_t>(CHUNK_PATHS, M - done);
         if (m == 0) break;
@@ -350,7 +416,23 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         xp.Z = dZ ? dZ + done * (uint64_t)N : nullptr;
         xp.S_out = d_S ? d_S + done : nullptr;
         xp.accum = e->d_accum;
-        if (var) {
+        if (plan.kernel == MCR_KERNEL_TENSOR) {
+            tl.M = m; tl.path_offset = path_offset + done; tl.S_out = xp.S_out;
+            const uint64_t tiles = (m + 127) / 128;
+            const int grid = (int)std::min<uint64_t>((uint64_t)tc_grid_full, tiles);
+            const bool timed = e->n_timed < MAX_TIMED_CHUNKS;
+            if (timed) MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed], s));
+            MCR_CUDA(tc_launch(N, tl, grid, s));
+            if (timed) { MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed + 1], s)); ++e->n_timed; }
+            ++launches;
+            if (plan.recheck) {
+                xp.flag_list = e->d_flag_list; xp.flag_count = e->d_flag_count; xp.flag_cap = FLAG_CAP;
+                MCR_CUDA(launch_exact(xp, e->num_sms, s));
+                ++launches;
+            }
+            fin.block_partials = e->d_block_partials; fin.n_blocks = grid;
+            fin.flag_count = e->d_flag_count; fin.flag_cap = FLAG_CAP;
+        } else if (var) {
             fp.M = m; fp.path_offset = path_offset + done;
             fp.Z = xp.Z; fp.S_out = xp.S_out;
             const uint64_t need = (m + 127) / 128;

@@ -36,6 +36,12 @@ struct mcr_engine {
     std::vector<std::vector<float>> packed;  // per variant index, filled lazily
     double* d_mu = nullptr;
     double* d_Acm = nullptr;
+    // tensor-core path: device copy of the split transform image and what it was built for
+    void* d_tc_image = nullptr;
+    size_t tc_image_cap = 0;
+    uint64_t tc_gen = 0;
+    double tc_x = 0;
+    std::vector<uint8_t> tc_host_image;
     double gamma_rowabs_max = 0;  // max_i gamma_i * sum_j |A_ij|
     // scratch
     uint32_t* d_flag_list = nullptr;

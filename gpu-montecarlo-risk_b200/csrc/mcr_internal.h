@@ -83,6 +83,28 @@ struct FinalizeParams {
 };
 cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t s);
 
+// ---- tensor-core path (mcr_tc.cu) -----------------------------------------------------------------
+struct TcLaunch {
+    uint64_t M, path_offset;
+    uint32_t key0, key1;
+    int32_t k;
+    float delta_rel, delta_abs;  // guard band = delta_rel * max_j|z_j| + delta_abs
+    const void* d_image;        // device copy of the split, swizzled transform image (tc_build)
+    int32_t* S_out;
+    uint32_t* flag_list;
+    uint32_t* flag_count;
+    uint32_t flag_cap;
+    uint64_t* block_partials;
+};
+int tc_max_n();
+bool tc_supported(int N);
+size_t tc_image_bytes(int N);
+int tc_padded_n(int N);
+// A: N x N row-major fp64 transform, c: N thresholds mu_i + x  ->  host image (tc_image_bytes)
+void tc_build(int N, const double* A, const double* c, uint8_t* image);
+cudaError_t tc_occupancy(int N, int* blocks_per_sm);
+cudaError_t tc_launch(int N, const TcLaunch& l, int grid, cudaStream_t s);
+
 cudaError_t launch_dump(uint64_t M, uint64_t path_offset, uint32_t key0, uint32_t key1, int N,
                         float* dZ, uint32_t* dU, cudaStream_t s);
 cudaError_t launch_fp32_peak(int grid, int iters, float* sink, cudaStream_t s);

@@ -1,0 +1,477 @@
+// The fused hot-path kernel, tensor-core flavour: batched correlate  D[128 x N] = Z[128 x K] * B^T
+// on the 5th-generation tensor cores (tcgen05.mma, accumulator in TMEM), normals staged in shared
+// memory only, threshold/count epilogue straight out of TMEM.
+//
+// Same pipeline as the FFMA kernel (mcr_ffma.cuh) and the reference trial
+// (src/02-C-serial/monte_carlo_serial.c:62-85), restructured as a real GEMM over a tile of 128 trials:
+//   generator warps : Philox4x32-10 -> Box-Muller normals z (registers) -> split z = z_hi + z_lo (fp16)
+//                     -> written K-major, 128-byte-swizzled into shared memory (never to HBM)
+//   MMA warp        : one elected thread issues  D  = Zhi*Bhi^T + Zhi*Blo^T + Zlo*Bhi^T   (fp16x3,
+//                     fp32 accumulate in TMEM); B = the transform, split the same way, resident in smem.
+//                     Column K-1.. holds the constant term: z[:, N] = 1 and B[i][N] = mu_i + x, so the
+//                     accumulator is directly  R_i + x  (padded rows get +1 and can never hit).
+//   epilogue        : the generator warps read their 32 TMEM lanes (tcgen05.ld), count sign bits,
+//                     track the guard band, and reduce like the FFMA kernel; near-threshold trials go
+//                     to the same fp64 fix-up list.
+// Why fp16x3 and not TF32x3: the split operands are half the size (Z tiles + B stay resident for
+// N <= 128) and hi + lo carries 22 significand bits, so the dropped lo*lo term is 2^-22 relative:
+// the guard band is about as narrow as the fp32 FFMA kernel's and the final counts remain
+// bit-identical to fp64 on the same normals.  (bf16x3 was tried first: 2^-16, four times as many
+// trials sent to the fp64 fix-up.)
+#include "mcr_internal.h"
+#include "mcr_rng.cuh"
+
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace mcr {
+
+namespace tc {
+
+constexpr int TILE_M = 128;        // trials per tile = UMMA M = TMEM lanes
+constexpr int KBLOCK = 64;         // fp16 elements per 128-byte swizzle row
+constexpr int GEN_THREADS = 128;   // warps 0..3: generator + epilogue (warp w owns TMEM lanes 32w..32w+31)
+constexpr int THREADS = GEN_THREADS + 32;  // + warp 4: TMEM allocation and MMA issue
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---- tcgen05 wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, fp16 inputs, fp32 accumulate, one CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): 8-row groups of
+// 128-byte rows, 1024 bytes apart (SBO); the 16-byte chunk index is XORed with (row % 8).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                       // descriptor version = 1 (Blackwell)
+    d |= (uint64_t)2 << 61;                       // layout type: SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4)        // c_format = F32; a_format = b_format = 0 (F16)
+           | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+// byte offset of element (row r, column k) inside an operand image made of K-blocks of [rows x 64] fp16
+__host__ __device__ inline uint32_t operand_offset(int rows, int r, int k) {
+    const int kb = k / KBLOCK, kk = k % KBLOCK;
+    return (uint32_t)kb * (uint32_t)rows * 128u + (uint32_t)(r / 8) * 1024u + (uint32_t)(r % 8) * 128u +
+           (uint32_t)(((kk / 8) ^ (r % 8)) * 16) + (uint32_t)(kk % 8) * 2u;
+}
+
+}  // namespace tc
+
+constexpr double TC_SCALE = 1024.0;  // 2^10, see tc_build_image
+
+struct TcParams {
+    uint64_t M, path_offset;
+    uint32_t key0, key1;
+    int32_t k, N;
+    float delta_rel, delta_abs;   // guard band = delta_rel * max_j |z_j| + delta_abs (0, 0 disables the recheck)
+    const uint4* B_image;   // global: [Bhi image | Blo image], each KB * NOUT * 128 bytes
+    int32_t* S_out;
+    uint32_t* flag_list;
+    uint32_t* flag_count;
+    uint32_t flag_cap;
+    uint64_t* block_partials;
+};
+
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+#ifndef MCR_TC_GROUPS_KB1
+#define MCR_TC_GROUPS_KB1 2   // generator warpgroups per CTA when K fits one 64-column block
+#endif
+#ifndef MCR_TC_UNROLL
+#define MCR_TC_UNROLL 2
+#endif
+constexpr int TC_UNROLL = MCR_TC_UNROLL;  // 8-normal chunks in flight per generator thread
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// split 8 normals into fp16 hi + lo and store them as one 16-byte chunk (chunk index c8) of the thread's
+// row in the K-major, 128-byte-swizzled operand images.  zhi_row / zlo_row: shared-space address of the
+// thread's row in K-block 0; r7s = (row % 8) << 4 (the swizzle XOR term).
+__device__ __forceinline__ void store_chunk(const float (&z)[8], int c8, uint32_t zhi_row, uint32_t zlo_row, uint32_t r7s, float& zmax) {
+    using namespace tc;
+    uint32_t hv[4], lv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        zmax = fmaxf(zmax, fmaxf(fabsf(z[2 * q]), fabsf(z[2 * q + 1])));
+        const __half2 h = __floats2half2_rn(z[2 * q], z[2 * q + 1]);
+        const float2 f = __half22float2(h);
+        const __half2 l = __floats2half2_rn(z[2 * q] - f.x, z[2 * q + 1] - f.y);
+        hv[q] = *reinterpret_cast<const uint32_t*>(&h);
+        lv[q] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    const uint32_t off = (uint32_t)(c8 >> 3) * (TILE_M * 128u) + ((((uint32_t)c8 & 7u) << 4) ^ r7s);
+    sts128(zhi_row + off, hv[0], hv[1], hv[2], hv[3]);
+    sts128(zlo_row + off, lv[0], lv[1], lv[2], lv[3]);
+}
+
+// NOUT   = transform rows padded to a multiple of 16 (UMMA N)
+// KB     = 64-column K-blocks (K = N + 1 padded)
+// GROUPS = generator warpgroups per CTA (1 or 2).  Each group owns a Z tile in shared memory and a
+//          TMEM accumulator; the single MMA warp serves them alternately, so one group's Philox /
+//          Box-Muller work overlaps the other group's MMA + TMEM epilogue.  The transform image is shared.
+template <int NOUT, int KB, int GROUPS>
+__global__ void __launch_bounds__(128 * GROUPS + 32) tc_path_kernel(const TcParams p) {
+    using namespace tc;
+    constexpr uint32_t Z_BYTES = KB * TILE_M * 128;   // one of Zhi / Zlo of one group
+    constexpr uint32_t B_BYTES = KB * NOUT * 128;     // one of Bhi / Blo
+    constexpr uint32_t GROUP_COLS = (NOUT + 31) & ~31;
+    constexpr uint32_t NEED_COLS = GROUP_COLS * GROUPS;
+    constexpr uint32_t TMEM_COLS = NEED_COLS <= 32 ? 32 : NEED_COLS <= 64 ? 64 : NEED_COLS <= 128 ? 128 : NEED_COLS <= 256 ? 256 : 512;
+    constexpr int NTHREADS = 128 * GROUPS + 32;
+    constexpr int MMA_WARP = 4 * GROUPS;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_z = smem;                                   // [group][hi|lo][Z_BYTES]
+    uint8_t* s_bhi = smem + 2 * GROUPS * Z_BYTES;
+    uint8_t* s_blo = s_bhi + B_BYTES;
+    __shared__ uint64_t s_bar[GROUPS];
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_cnt[4 * GROUPS], s_sum[4 * GROUPS];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- one-time setup: transform into smem, Z buffers zeroed with the constant column = 1.0 ----
+    {
+        const uint4* src = p.B_image;
+        uint4* dst = reinterpret_cast<uint4*>(s_bhi);
+        for (uint32_t t = tid; t < 2 * B_BYTES / 16; t += NTHREADS) dst[t] = src[t];
+        uint4* zz = reinterpret_cast<uint4*>(s_z);
+        for (uint32_t t = tid; t < 2 * GROUPS * Z_BYTES / 16; t += NTHREADS) zz[t] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    if (tid < 128 * GROUPS)
+        *reinterpret_cast<__half*>(s_z + (tid / 128) * 2 * Z_BYTES + operand_offset(TILE_M, tid % 128, p.N)) = __float2half_rn(1.0f);
+    if (tid == 0)
+        for (int gg = 0; gg < GROUPS; ++gg) mbar_init(&s_bar[gg], 1);
+    if (warp == MMA_WARP) tmem_alloc(&s_tmem, TMEM_COLS);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+
+    const uint64_t n_tiles = (p.M + TILE_M - 1) / TILE_M;
+    constexpr uint32_t IDESC = make_idesc(NOUT);
+    uint32_t cnt = 0, sum_s = 0;
+
+    if (warp == MMA_WARP) {
+        // ---- MMA warp: serve the groups' tiles in order n = 0, 1, 2, ... (group = n % GROUPS) ----
+        uint32_t n = 0;
+        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+            const int g = n % GROUPS;
+            named_bar_sync(1 + g, 160);   // group g's Z tile is complete and visible to the async proxy
+            if (lane == 0) {
+                tc_fence_after();
+                const uint32_t zhi = smem_u32(s_z + g * 2 * Z_BYTES), zlo = zhi + Z_BYTES;
+                const uint32_t bhi = smem_u32(s_bhi), blo = smem_u32(s_blo);
+                const uint32_t d_tmem = tmem_base + g * GROUP_COLS;
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t za = pass == 2 ? zlo : zhi;
+                    const uint32_t ba = pass == 1 ? blo : bhi;
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                        for (int ks = 0; ks < KBLOCK / 16; ++ks) {
+                            umma_f16(d_tmem, make_desc(za + kb * (TILE_M * 128) + ks * 32),
+                                      make_desc(ba + kb * (NOUT * 128) + ks * 32), IDESC, acc);
+                            acc = 1;
+                        }
+                }
+                umma_commit(&s_bar[g]);   // arrives on the group's mbarrier when these MMAs have completed
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---- generator + epilogue warps ----
+        const int g = warp / 4;
+        const int row = tid - 128 * g;
+        const uint32_t zhi_row = smem_u32(s_z + g * 2 * Z_BYTES) + (uint32_t)(row / 8) * 1024u + (uint32_t)(row % 8) * 128u;
+        const uint32_t zlo_row = zhi_row + Z_BYTES;
+        const uint32_t r7s = (uint32_t)(row % 8) << 4;
+        const uint32_t taddr = tmem_base + g * GROUP_COLS + ((uint32_t)((warp % 4) * 32) << 16);
+        uint32_t phase = 0, n = 0;
+        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+            if ((int)(n % GROUPS) != g) continue;
+            const uint64_t i = tile * TILE_M + row;   // chunk-relative trial index of this thread
+            const uint64_t path = p.path_offset + i;
+            PhiloxPath rng;
+            rng.init((uint32_t)path, (uint32_t)(path >> 32), p.key1);
+            float zmax = 0.0f;
+            // full 16-byte chunks: two Philox blocks = 8 normals = one chunk of the row (conflict-free
+            // STS.128); nothing but RNG + split + store in this loop
+            const int n_full = p.N / 8;
+            int c8 = 0;
+            for (; c8 + TC_UNROLL <= n_full; c8 += TC_UNROLL) {
+                float z[8 * TC_UNROLL];
+                rng.normals_multi<2 * TC_UNROLL>((uint32_t)(2 * c8), p.key0, p.key1, z);
+#pragma unroll
+                for (int u = 0; u < TC_UNROLL; ++u) {
+                    float zc[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) zc[q] = z[8 * u + q];
+                    store_chunk(zc, c8 + u, zhi_row, zlo_row, r7s, zmax);
+                }
+            }
+            for (; c8 < n_full; ++c8) {
+                float z[8];
+                rng.normals_multi<2>((uint32_t)(2 * c8), p.key0, p.key1, z);
+                store_chunk(z, c8, zhi_row, zlo_row, r7s, zmax);
+            }
+            // tail chunk: the remaining normals (if any), the constant 1 in column N, zeros beyond
+            {
+                float z[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) z[q] = 0.0f;
+                if (8 * n_full < p.N) rng.normals((uint32_t)(2 * n_full), p.key0, p.key1, z);
+                if (8 * n_full + 4 < p.N) rng.normals((uint32_t)(2 * n_full + 1), p.key0, p.key1, z + 4);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (8 * n_full + q == p.N) z[q] = 1.0f;
+                    if (8 * n_full + q > p.N) z[q] = 0.0f;
+                }
+                float zmax_tail = 0.0f;   // the constant column must not enter max|z|
+                store_chunk(z, n_full, zhi_row, zlo_row, r7s, zmax_tail);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (8 * n_full + q < p.N) zmax = fmaxf(zmax, fabsf(z[q]));
+            }
+            fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core
+            named_bar_arrive(1 + g, 160);  // hand the tile to the MMA warp (no wait here)
+
+            // ---- epilogue: wait for the MMAs, TMEM -> registers, threshold + guard band ----
+            mbar_wait(&s_bar[g], phase);
+            phase ^= 1;
+            tc_fence_after();
+            uint32_t S = 0;
+            float band = 3.0e38f;
+#pragma unroll
+            for (int c0 = 0; c0 < NOUT; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if (c0 + c < NOUT) {
+                        S += v[c] >> 31;
+                        band = fminf(band, fabsf(__uint_as_float(v[c])));
+                    }
+                }
+            }
+            tc_fence_before();
+            if (i < p.M) {
+                if (band < __fmaf_rn(p.delta_rel, zmax, p.delta_abs)) {
+                    const uint32_t slot = atomicAdd(p.flag_count, 1u);
+                    if (slot < p.flag_cap) p.flag_list[slot] = (uint32_t)i;
+                } else {
+                    cnt += (S >= (uint32_t)p.k) ? 1u : 0u;
+                    sum_s += S;
+                    if (p.S_out) p.S_out[i] = (int32_t)S;
+                }
+            }
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        sum_s = __reduce_add_sync(0xffffffffu, sum_s);
+        if (lane == 0) { s_cnt[warp] = cnt; s_sum[warp] = sum_s; }
+    }
+
+    // ---- block reduction + teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t c = 0, s = 0;
+        for (int w = 0; w < 4 * GROUPS; ++w) { c += s_cnt[w]; s += s_sum[w]; }
+        p.block_partials[2 * (uint64_t)blockIdx.x] = c;
+        p.block_partials[2 * (uint64_t)blockIdx.x + 1] = s;
+    }
+    if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+// Transform image: rows i < N hold A_ij * 2^10 (columns j < N) and (mu_i + x) * 2^10 (column N); padded
+// rows hold +2^10 in column N so they are always far on the "no crash" side.  Everything is split into
+// fp16 hi + lo.  The 2^10 scale only moves the values (|A| ~ 1e-2, lo parts ~ 1e-6) out of fp16's
+// subnormal range; signs and the (equally scaled) guard band are unaffected.
+template <int NOUT, int KB>
+static void tc_build_image(const double* A, const double* c, int N, uint8_t* image) {
+    const size_t bytes = (size_t)KB * NOUT * 128;
+    memset(image, 0, 2 * bytes);
+    for (int i = 0; i < NOUT; ++i)
+        for (int k = 0; k <= N; ++k) {
+            double v;
+            if (k < N) v = (i < N) ? A[(size_t)i * N + k] : 0.0;
+            else v = (i < N) ? c[i] : 1.0;
+            v *= TC_SCALE;
+            const __half hi = __float2half_rn((float)v);
+            const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+            const uint32_t off = tc::operand_offset(NOUT, i, k);
+            memcpy(image + off, &hi, 2);
+            memcpy(image + bytes + off, &lo, 2);
+        }
+}
+
+template <int NOUT, int KB, int GROUPS>
+static size_t tc_smem_bytes() { return 2 * (size_t)GROUPS * KB * tc::TILE_M * 128 + 2 * (size_t)KB * NOUT * 128 + 1024; }
+
+template <int NOUT, int KB, int GROUPS>
+static cudaError_t tc_prepare() {
+    // opt in to the large dynamic shared memory and the largest carveout (several CTAs per SM overlap
+    // each other's bubbles); both are per-device function attributes, cheap to set repeatedly
+    cudaError_t e = cudaFuncSetAttribute(tc_path_kernel<NOUT, KB, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)tc_smem_bytes<NOUT, KB, GROUPS>());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc_path_kernel<NOUT, KB, GROUPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+template <int NOUT, int KB, int GROUPS>
+static cudaError_t tc_launch_impl(const TcParams& p, int grid, cudaStream_t s) {
+    cudaError_t e = tc_prepare<NOUT, KB, GROUPS>();
+    if (e != cudaSuccess) return e;
+    tc_path_kernel<NOUT, KB, GROUPS><<<grid, 128 * GROUPS + 32, tc_smem_bytes<NOUT, KB, GROUPS>(), s>>>(p);
+    return cudaGetLastError();
+}
+
+// CTAs that fit one SM.  Computed here because cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1
+// for this kernel although the hardware co-schedules more (measured: 4 CTAs/SM run 2.2x faster than 1):
+// shared memory, TMEM columns (512 per SM), threads and registers bound it.
+template <int NOUT, int KB, int GROUPS>
+static cudaError_t tc_occupancy_impl(int* bps) {
+    cudaError_t e = tc_prepare<NOUT, KB, GROUPS>();
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa{};
+    e = cudaFuncGetAttributes(&fa, tc_path_kernel<NOUT, KB, GROUPS>);
+    if (e != cudaSuccess) return e;
+    int dev = 0, smem_sm = 0, regs_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    constexpr int threads = 128 * GROUPS + 32;
+    constexpr uint32_t group_cols = (NOUT + 31) & ~31, need = group_cols * GROUPS;
+    constexpr int tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+    const size_t per_cta = tc_smem_bytes<NOUT, KB, GROUPS>() + fa.sharedSizeBytes + 1024;  // + driver reservation
+    int n = (int)(smem_sm / per_cta);
+    n = std::min(n, 512 / tmem_cols);
+    n = std::min(n, 2048 / threads);
+    n = std::min(n, regs_sm / (((fa.numRegs + 7) & ~7) * ((threads + 31) & ~31)));
+    *bps = std::max(n, 0);
+    if (getenv("MCR_DEBUG"))
+        fprintf(stderr, "[mcr] tc_path_kernel<%d,%d,%d>: %d CTAs/SM (dyn smem %zu, static %zu, regs %d, tmem cols %d)\n",
+                NOUT, KB, GROUPS, *bps, tc_smem_bytes<NOUT, KB, GROUPS>(), fa.sharedSizeBytes, fa.numRegs, tmem_cols);
+    return cudaSuccess;
+}
+
+struct TcVariant {
+    int nout, kb, groups;
+    size_t image_bytes;
+    void (*build)(const double*, const double*, int, uint8_t*);
+    cudaError_t (*launch)(const TcParams&, int, cudaStream_t);
+    cudaError_t (*occupancy)(int*);
+};
+
+template <int NOUT, int KB, int GROUPS>
+static TcVariant tc_variant() {
+    return TcVariant{NOUT, KB, GROUPS, 2 * (size_t)KB * NOUT * 128, &tc_build_image<NOUT, KB>, &tc_launch_impl<NOUT, KB, GROUPS>,
+                     &tc_occupancy_impl<NOUT, KB, GROUPS>};
+}
+
+// smallest instantiation with nout >= N and 64 * kb >= N + 1
+static const TcVariant* tc_find(int N) {
+    static const TcVariant table[] = {
+        tc_variant<16, 1, MCR_TC_GROUPS_KB1>(), tc_variant<32, 1, MCR_TC_GROUPS_KB1>(), tc_variant<48, 1, MCR_TC_GROUPS_KB1>(),
+        tc_variant<64, 1, MCR_TC_GROUPS_KB1>(), tc_variant<64, 2, 2>(),
+        tc_variant<80, 2, 2>(), tc_variant<96, 2, 2>(), tc_variant<112, 2, 2>(), tc_variant<128, 2, 2>(), tc_variant<128, 3, 1>(),
+    };
+    for (const TcVariant& v : table)
+        if (v.nout >= N && 64 * v.kb >= N + 1) return &v;
+    return nullptr;
+}
+
+int tc_max_n() { return 128; }
+
+bool tc_supported(int N) { return tc_find(N) != nullptr; }
+
+size_t tc_image_bytes(int N) { const TcVariant* v = tc_find(N); return v ? v->image_bytes : 0; }
+
+int tc_padded_n(int N) { const TcVariant* v = tc_find(N); return v ? v->nout : 0; }
+
+void tc_build(int N, const double* A, const double* c, uint8_t* image) { tc_find(N)->build(A, c, N, image); }
+
+cudaError_t tc_occupancy(int N, int* bps) { return tc_find(N)->occupancy(bps); }
+
+cudaError_t tc_launch(int N, const TcLaunch& l, int grid, cudaStream_t s) {
+    TcParams p{};
+    p.M = l.M; p.path_offset = l.path_offset; p.key0 = l.key0; p.key1 = l.key1; p.k = l.k; p.N = N;
+    p.delta_rel = (float)(l.delta_rel * TC_SCALE); p.delta_abs = (float)(l.delta_abs * TC_SCALE);  // accumulators are scaled
+    p.B_image = reinterpret_cast<const uint4*>(l.d_image); p.S_out = l.S_out;
+    p.flag_list = l.flag_list; p.flag_count = l.flag_count; p.flag_cap = l.flag_cap; p.block_partials = l.block_partials;
+    return tc_find(N)->launch(p, grid, s);
+}
+
+}  // namespace mcr

@@ -137,17 +137,17 @@ def test_philox_run_bit_exact_vs_oracle_on_dumped_normals(engine, oracle, N, mod
     seed, off = 67, 1000003
     Z, _ = engine.dump_normals(M, seed, path_offset=off)
     ro = oracle.run_normals(A, mu, k, x, Z)
-    r = engine.run(M, seed, x, k, path_offset=off)
-    assert r.kernel == "ffma" and r.padded_N >= N
-    assert (r.count, r.sum_S, r.n_paths) == (ro["count"], ro["sum_S"], M)
-    rx = engine.run(M, seed, x, k, path_offset=off, kernel=api.KERNEL_EXACT)
-    assert (rx.count, rx.sum_S) == (ro["count"], ro["sum_S"])
-    h = api.simulate_host(mu, A, M, seed, x, k, a_is_lower=(mode == api.TRANSFORM_LOWER), want_S_values=True)
-    # simulate_host starts at path 0: compare with its own dump
+    for kernel, name in ((api.KERNEL_FFMA, "ffma"), (api.KERNEL_TENSOR, "tensor"), (api.KERNEL_EXACT, "exact"), (api.KERNEL_AUTO, None)):
+        r = engine.run(M, seed, x, k, path_offset=off, kernel=kernel)
+        assert (name is None or r.kernel == name) and r.padded_N >= N
+        assert (r.count, r.sum_S, r.n_paths) == (ro["count"], ro["sum_S"], M), (r.kernel, r)
+    # simulate_host starts at path 0: compare with its own dump; S_values from both fast kernels
     Z0, _ = engine.dump_normals(M, seed)
     r0 = oracle.run_normals(A, mu, k, x, Z0)
-    np.testing.assert_array_equal(h.S_values, r0["S_values"])
-    assert (h.count, h.sum_S) == (r0["count"], r0["sum_S"])
+    for kernel in (api.KERNEL_FFMA, api.KERNEL_TENSOR):
+        h = api.simulate_host(mu, A, M, seed, x, k, a_is_lower=(mode == api.TRANSFORM_LOWER), want_S_values=True, kernel=kernel)
+        np.testing.assert_array_equal(h.S_values, r0["S_values"])
+        assert (h.count, h.sum_S) == (r0["count"], r0["sum_S"])
 
 
 def test_independent_streams_agree_within_3_sigma(engine, oracle):
@@ -218,6 +218,35 @@ def test_edge_cases(engine, oracle):
     assert r.count == 0 and r.sum_S == 0
 
 
+def test_tensor_kernel_raw_decisions_are_close_and_recheck_makes_them_exact(engine, oracle):
+    """fp16x3 tensor-core correlate: without the fp64 recheck a handful of near-threshold decisions may
+    differ from fp64 (stated tolerance: at most 1e-5 of the per-asset decisions); with it, none."""
+    for N in (50, 100, 128):
+        mu, Sigma, x, k = model(N)
+        A = engine.upload_sigma(mu, Sigma)
+        M = 400000
+        Z, _ = engine.dump_normals(M, 31337)
+        ro = oracle.run_normals(A, mu, k, x, Z)
+        raw = api.simulate_host(mu, A, M, 31337, x, k, a_is_lower=True, want_S_values=True, kernel=api.KERNEL_TENSOR, no_recheck=True)
+        assert raw.n_rechecked == 0
+        assert np.abs(raw.S_values.astype(np.int64) - ro["S_values"]).sum() <= 1e-5 * M * N
+        fix = api.simulate_host(mu, A, M, 31337, x, k, a_is_lower=True, want_S_values=True, kernel=api.KERNEL_TENSOR)
+        np.testing.assert_array_equal(fix.S_values, ro["S_values"])
+        assert 0 < fix.n_rechecked < M // 50
+
+
+def test_kernel_selection(engine):
+    mu, Sigma, x, k = model(15)
+    engine.upload_sigma(mu, Sigma)
+    assert engine.run(1000, 1, x, k).kernel == "ffma"          # small N: FFMA kernel
+    m = synthetic_model(64)
+    engine.upload_sigma(m.mu, m.Sigma)
+    assert engine.run(1000, 1, m.x, m.k).kernel == "tensor"    # N >= 36: tensor-core kernel
+    Z = np.zeros((4, 64))
+    with pytest.raises(api.McrError, match="tensor-core kernel generates its normals"):
+        engine.run_with_normals(Z, m.x, m.k, kernel=api.KERNEL_TENSOR)
+
+
 def test_large_n_falls_back_to_gpu_exact_kernel(engine, oracle):
     m = synthetic_model(160)
     A = engine.upload_sigma(m.mu, m.Sigma)
@@ -227,6 +256,8 @@ def test_large_n_falls_back_to_gpu_exact_kernel(engine, oracle):
     assert r.kernel == "exact" and (r.count, r.sum_S) == (ro["count"], ro["sum_S"])
     with pytest.raises(api.McrError, match="no FFMA instantiation"):
         engine.run(5000, 11, m.x, m.k, kernel=api.KERNEL_FFMA)
+    with pytest.raises(api.McrError, match="tensor-core kernel covers"):
+        engine.run(5000, 11, m.x, m.k, kernel=api.KERNEL_TENSOR)
 
 
 def test_error_behaviour():
