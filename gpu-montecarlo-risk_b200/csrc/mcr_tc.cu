@@ -137,8 +137,11 @@ struct TcParams {
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-#ifndef MCR_TC_GROUPS_KB1
-#define MCR_TC_GROUPS_KB1 2   // generator warpgroups per CTA when K fits one 64-column block
+#ifndef MCR_TC_ABLATE
+#define MCR_TC_ABLATE 0
+#endif
+#ifndef MCR_TC_GROUPS
+#define MCR_TC_GROUPS 3   // generator warpgroups per CTA while 2 accumulator regions per group fit TMEM (NOUT <= 64)
 #endif
 #ifndef MCR_TC_UNROLL
 #define MCR_TC_UNROLL 2
@@ -154,6 +157,12 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 // thread's row in K-block 0; r7s = (row % 8) << 4 (the swizzle XOR term).
 __device__ __forceinline__ void store_chunk(const float (&z)[8], int c8, uint32_t zhi_row, uint32_t zlo_row, uint32_t r7s, float& zmax) {
     using namespace tc;
+#if MCR_TC_ABLATE == 1   // tuning only: RNG without split / store
+#pragma unroll
+    for (int q = 0; q < 8; ++q) zmax = fmaxf(zmax, fabsf(z[q]));
+    if (zmax == 123.0f) sts128(zhi_row, 0, 0, 0, 0);
+    return;
+#endif
     uint32_t hv[4], lv[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -164,51 +173,56 @@ __device__ __forceinline__ void store_chunk(const float (&z)[8], int c8, uint32_
         hv[q] = *reinterpret_cast<const uint32_t*>(&h);
         lv[q] = *reinterpret_cast<const uint32_t*>(&l);
     }
-    const uint32_t off = (uint32_t)(c8 >> 3) * (TILE_M * 128u) + ((((uint32_t)c8 & 7u) << 4) ^ r7s);
+    const uint32_t off = (((uint32_t)c8 & 7u) << 4) ^ r7s;   // c8: chunk index inside the K-block
     sts128(zhi_row + off, hv[0], hv[1], hv[2], hv[3]);
     sts128(zlo_row + off, lv[0], lv[1], lv[2], lv[3]);
 }
 
 // NOUT   = transform rows padded to a multiple of 16 (UMMA N)
 // KB     = 64-column K-blocks (K = N + 1 padded)
-// GROUPS = generator warpgroups per CTA (1 or 2).  Each group owns a Z tile in shared memory and a
-//          TMEM accumulator; the single MMA warp serves them alternately, so one group's Philox /
-//          Box-Muller work overlaps the other group's MMA + TMEM epilogue.  The transform image is shared.
+// GROUPS = generator warpgroups per CTA.
+//
+// Pipeline (per group; the single MMA warp serves the groups round-robin):
+//   * Z is produced one K-block (128 trials x 64 columns, fp16 hi + lo = 32 KB) at a time into a ring of
+//     two shared-memory slots; a slot is handed to the MMA warp through a named barrier ("full") and
+//     comes back through an mbarrier the MMA warp commits to ("empty").  Shared memory per group is
+//     therefore 64 KB whatever K is.
+//   * every tile accumulates into one of two TMEM regions of the group; the MMA warp commits to a
+//     "done" mbarrier after the tile's last K-block.
+//   * the epilogue of tile n runs AFTER the group has generated tile n+1, so it never waits for the
+//     tensor core in steady state: the generator warps issue Philox/Box-Muller work back to back.
 template <int NOUT, int KB, int GROUPS>
-__global__ void __launch_bounds__(128 * GROUPS + 32) tc_path_kernel(const TcParams p) {
+__global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcParams p) {
     using namespace tc;
-    constexpr uint32_t Z_BYTES = KB * TILE_M * 128;   // one of Zhi / Zlo of one group
-    constexpr uint32_t B_BYTES = KB * NOUT * 128;     // one of Bhi / Blo
-    constexpr uint32_t GROUP_COLS = (NOUT + 31) & ~31;
-    constexpr uint32_t NEED_COLS = GROUP_COLS * GROUPS;
+    constexpr uint32_t SLOT_BYTES = 2 * TILE_M * 128;   // one K-block of Z: hi then lo
+    constexpr uint32_t B_BYTES = KB * NOUT * 128;       // one of Bhi / Blo
+    constexpr uint32_t GROUP_COLS = (NOUT + 31) & ~31;  // TMEM columns of one accumulator region
+    constexpr uint32_t NEED_COLS = 2 * GROUP_COLS * GROUPS;
     constexpr uint32_t TMEM_COLS = NEED_COLS <= 32 ? 32 : NEED_COLS <= 64 ? 64 : NEED_COLS <= 128 ? 128 : NEED_COLS <= 256 ? 256 : 512;
+    static_assert(NEED_COLS <= 512, "accumulators do not fit TMEM");
     constexpr int NTHREADS = 128 * GROUPS + 32;
     constexpr int MMA_WARP = 4 * GROUPS;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* s_z = smem;                                   // [group][hi|lo][Z_BYTES]
-    uint8_t* s_bhi = smem + 2 * GROUPS * Z_BYTES;
+    uint8_t* s_ring = smem;                                   // [group][slot][hi|lo][128 x 128 B]
+    uint8_t* s_bhi = smem + 2 * GROUPS * SLOT_BYTES;
     uint8_t* s_blo = s_bhi + B_BYTES;
-    __shared__ uint64_t s_bar[GROUPS];
+    __shared__ uint64_t s_empty[GROUPS][2], s_done[GROUPS][2];
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_cnt[4 * GROUPS], s_sum[4 * GROUPS];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- one-time setup: transform into smem, Z buffers zeroed with the constant column = 1.0 ----
+    // ---- one-time setup ----
     {
         const uint4* src = p.B_image;
         uint4* dst = reinterpret_cast<uint4*>(s_bhi);
         for (uint32_t t = tid; t < 2 * B_BYTES / 16; t += NTHREADS) dst[t] = src[t];
-        uint4* zz = reinterpret_cast<uint4*>(s_z);
-        for (uint32_t t = tid; t < 2 * GROUPS * Z_BYTES / 16; t += NTHREADS) zz[t] = make_uint4(0, 0, 0, 0);
     }
-    __syncthreads();
-    if (tid < 128 * GROUPS)
-        *reinterpret_cast<__half*>(s_z + (tid / 128) * 2 * Z_BYTES + operand_offset(TILE_M, tid % 128, p.N)) = __float2half_rn(1.0f);
     if (tid == 0)
-        for (int gg = 0; gg < GROUPS; ++gg) mbar_init(&s_bar[gg], 1);
+        for (int gg = 0; gg < GROUPS; ++gg)
+            for (int b = 0; b < 2; ++b) { mbar_init(&s_empty[gg][b], 1); mbar_init(&s_done[gg][b], 1); }
     if (warp == MMA_WARP) tmem_alloc(&s_tmem, TMEM_COLS);
     fence_async_smem();
     tc_fence_before();
@@ -217,105 +231,75 @@ __global__ void __launch_bounds__(128 * GROUPS + 32) tc_path_kernel(const TcPara
     const uint32_t tmem_base = s_tmem;
 
     const uint64_t n_tiles = (p.M + TILE_M - 1) / TILE_M;
+    // tiles of this CTA: global tile = blockIdx.x + gridDim.x * m, m = 0, 1, ...; group = m % GROUPS
+    const uint64_t cta_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     constexpr uint32_t IDESC = make_idesc(NOUT);
     uint32_t cnt = 0, sum_s = 0;
 
     if (warp == MMA_WARP) {
-        // ---- MMA warp: serve the groups' tiles in order n = 0, 1, 2, ... (group = n % GROUPS) ----
-        uint32_t n = 0;
-        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-            const int g = n % GROUPS;
-            named_bar_sync(1 + g, 160);   // group g's Z tile is complete and visible to the async proxy
-            if (lane == 0) {
-                tc_fence_after();
-                const uint32_t zhi = smem_u32(s_z + g * 2 * Z_BYTES), zlo = zhi + Z_BYTES;
-                const uint32_t bhi = smem_u32(s_bhi), blo = smem_u32(s_blo);
-                const uint32_t d_tmem = tmem_base + g * GROUP_COLS;
-                uint32_t acc = 0;
+        // ---- MMA warp: K-block u of group g, round-robin over g, in the order the groups produce them ----
+        uint64_t group_tiles[GROUPS];
+        uint64_t max_tiles = 0;
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t za = pass == 2 ? zlo : zhi;
-                    const uint32_t ba = pass == 1 ? blo : bhi;
+        for (int g = 0; g < GROUPS; ++g) {
+            group_tiles[g] = cta_tiles > (uint64_t)g ? (cta_tiles - g + GROUPS - 1) / GROUPS : 0;
+            max_tiles = group_tiles[g] > max_tiles ? group_tiles[g] : max_tiles;
+        }
+        const uint32_t bhi = smem_u32(s_bhi), blo = smem_u32(s_blo);
+        for (uint64_t n = 0; n < max_tiles; ++n) {
+#pragma unroll 1
+            for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
-                    for (int kb = 0; kb < KB; ++kb)
+                for (int g = 0; g < GROUPS; ++g) {
+                    if (n >= group_tiles[g]) continue;
+                    const uint32_t u = (uint32_t)(n * KB + kb), slot = u & 1;
+                    named_bar_sync(1 + 2 * g + slot, 160);   // the slot is full and visible to the async proxy
+                    if (lane == 0) {
+                        tc_fence_after();
+                        const uint32_t zhi = smem_u32(s_ring + (2 * g + slot) * SLOT_BYTES), zlo = zhi + TILE_M * 128;
+                        const uint32_t d_tmem = tmem_base + (2 * g + (uint32_t)(n & 1)) * GROUP_COLS;
 #pragma unroll
-                        for (int ks = 0; ks < KBLOCK / 16; ++ks) {
-                            umma_f16(d_tmem, make_desc(za + kb * (TILE_M * 128) + ks * 32),
-                                      make_desc(ba + kb * (NOUT * 128) + ks * 32), IDESC, acc);
-                            acc = 1;
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t za = pass == 2 ? zlo : zhi;
+                            const uint32_t ba = (pass == 1 ? blo : bhi) + kb * (NOUT * 128);
+#pragma unroll
+                            for (int ks = 0; ks < (MCR_TC_ABLATE == 3 ? 0 : KBLOCK / 16); ++ks)
+                                umma_f16(d_tmem, make_desc(za + ks * 32), make_desc(ba + ks * 32), IDESC,
+                                         (kb | pass | ks) != 0 ? 1u : 0u);
                         }
+                        umma_commit(&s_empty[g][slot]);                  // slot may be overwritten once these MMAs are done
+                        if (kb == KB - 1) umma_commit(&s_done[g][n & 1]); // ... and the tile's accumulator is complete
+                    }
+                    __syncwarp();
                 }
-                umma_commit(&s_bar[g]);   // arrives on the group's mbarrier when these MMAs have completed
             }
-            __syncwarp();
         }
     } else {
         // ---- generator + epilogue warps ----
         const int g = warp / 4;
         const int row = tid - 128 * g;
-        const uint32_t zhi_row = smem_u32(s_z + g * 2 * Z_BYTES) + (uint32_t)(row / 8) * 1024u + (uint32_t)(row % 8) * 128u;
-        const uint32_t zlo_row = zhi_row + Z_BYTES;
+        const uint32_t ring_row = smem_u32(s_ring + 2 * g * SLOT_BYTES) + (uint32_t)(row / 8) * 1024u + (uint32_t)(row % 8) * 128u;
         const uint32_t r7s = (uint32_t)(row % 8) << 4;
-        const uint32_t taddr = tmem_base + g * GROUP_COLS + ((uint32_t)((warp % 4) * 32) << 16);
-        uint32_t phase = 0, n = 0;
-        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-            if ((int)(n % GROUPS) != g) continue;
-            const uint64_t i = tile * TILE_M + row;   // chunk-relative trial index of this thread
-            const uint64_t path = p.path_offset + i;
-            PhiloxPath rng;
-            rng.init((uint32_t)path, (uint32_t)(path >> 32), p.key1);
-            float zmax = 0.0f;
-            // full 16-byte chunks: two Philox blocks = 8 normals = one chunk of the row (conflict-free
-            // STS.128); nothing but RNG + split + store in this loop
-            const int n_full = p.N / 8;
-            int c8 = 0;
-            for (; c8 + TC_UNROLL <= n_full; c8 += TC_UNROLL) {
-                float z[8 * TC_UNROLL];
-                rng.normals_multi<2 * TC_UNROLL>((uint32_t)(2 * c8), p.key0, p.key1, z);
-#pragma unroll
-                for (int u = 0; u < TC_UNROLL; ++u) {
-                    float zc[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) zc[q] = z[8 * u + q];
-                    store_chunk(zc, c8 + u, zhi_row, zlo_row, r7s, zmax);
-                }
-            }
-            for (; c8 < n_full; ++c8) {
-                float z[8];
-                rng.normals_multi<2>((uint32_t)(2 * c8), p.key0, p.key1, z);
-                store_chunk(z, c8, zhi_row, zlo_row, r7s, zmax);
-            }
-            // tail chunk: the remaining normals (if any), the constant 1 in column N, zeros beyond
-            {
-                float z[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) z[q] = 0.0f;
-                if (8 * n_full < p.N) rng.normals((uint32_t)(2 * n_full), p.key0, p.key1, z);
-                if (8 * n_full + 4 < p.N) rng.normals((uint32_t)(2 * n_full + 1), p.key0, p.key1, z + 4);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (8 * n_full + q == p.N) z[q] = 1.0f;
-                    if (8 * n_full + q > p.N) z[q] = 0.0f;
-                }
-                float zmax_tail = 0.0f;   // the constant column must not enter max|z|
-                store_chunk(z, n_full, zhi_row, zlo_row, r7s, zmax_tail);
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (8 * n_full + q < p.N) zmax = fmaxf(zmax, fabsf(z[q]));
-            }
-            fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core
-            named_bar_arrive(1 + g, 160);  // hand the tile to the MMA warp (no wait here)
+        const uint32_t taddr_g = tmem_base + 2 * g * GROUP_COLS + ((uint32_t)((warp % 4) * 32) << 16);
+        const uint64_t my_tiles = cta_tiles > (uint64_t)g ? (cta_tiles - g + GROUPS - 1) / GROUPS : 0;
+        const int n_full = p.N / 8;       // chunks (8 columns) made of normals only
+        uint32_t empty_phase = 0;         // bit s: parity to wait for on s_empty[g][s]
+        uint32_t done_phase = 0;          // bit r: parity to wait for on s_done[g][r]
+        float prev_zmax = 0.0f;
+        uint64_t prev_i = 0;
 
-            // ---- epilogue: wait for the MMAs, TMEM -> registers, threshold + guard band ----
-            mbar_wait(&s_bar[g], phase);
-            phase ^= 1;
+        // epilogue of local tile n (accumulator region n & 1): TMEM -> registers, threshold + guard band
+        auto epilogue = [&](uint64_t n, uint64_t i, float zmax) {
+            const uint32_t r = (uint32_t)(n & 1);
+            mbar_wait(&s_done[g][r], (done_phase >> r) & 1u);
+            done_phase ^= 1u << r;
             tc_fence_after();
             uint32_t S = 0;
             float band = 3.0e38f;
 #pragma unroll
-            for (int c0 = 0; c0 < NOUT; c0 += 32) {
+            for (int c0 = 0; c0 < (MCR_TC_ABLATE == 2 ? 0 : NOUT); c0 += 32) {
                 uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
+                tmem_ld32(taddr_g + r * GROUP_COLS + c0, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -336,7 +320,66 @@ __global__ void __launch_bounds__(128 * GROUPS + 32) tc_path_kernel(const TcPara
                     if (p.S_out) p.S_out[i] = (int32_t)S;
                 }
             }
+        };
+
+        for (uint64_t n = 0; n < my_tiles; ++n) {
+            const uint64_t tile = blockIdx.x + (uint64_t)gridDim.x * (n * GROUPS + g);
+            const uint64_t i = tile * TILE_M + row;   // chunk-relative trial index of this thread
+            const uint64_t path = p.path_offset + i;
+            PhiloxPath rng;
+            rng.init((uint32_t)path, (uint32_t)(path >> 32), p.key1);
+            float zmax = 0.0f;
+#pragma unroll 1
+            for (int kb = 0; kb < KB; ++kb) {
+                const uint32_t u = (uint32_t)(n * KB + kb), slot = u & 1;
+                if (u >= 2) {   // wait until the MMAs that read this slot two K-blocks ago have completed
+                    mbar_wait(&s_empty[g][slot], (empty_phase >> slot) & 1u);
+                    empty_phase ^= 1u << slot;
+                }
+                const uint32_t zhi_row = ring_row + slot * SLOT_BYTES, zlo_row = zhi_row + TILE_M * 128;
+                // chunks 8*kb .. 8*kb+7 of the row: normals, then the constant 1 in column N, zeros beyond
+                const int c_begin = 8 * kb;
+                int c8 = c_begin;
+                for (; c8 + TC_UNROLL <= min(n_full, c_begin + 8); c8 += TC_UNROLL) {
+                    float z[8 * TC_UNROLL];
+                    rng.normals_multi<2 * TC_UNROLL>((uint32_t)(2 * c8), p.key0, p.key1, z);
+#pragma unroll
+                    for (int w = 0; w < TC_UNROLL; ++w) {
+                        float zc[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) zc[q] = z[8 * w + q];
+                        store_chunk(zc, c8 + w - c_begin, zhi_row, zlo_row, r7s, zmax);
+                    }
+                }
+                for (; c8 < min(n_full, c_begin + 8); ++c8) {
+                    float z[8];
+                    rng.normals_multi<2>((uint32_t)(2 * c8), p.key0, p.key1, z);
+                    store_chunk(z, c8 - c_begin, zhi_row, zlo_row, r7s, zmax);
+                }
+                for (; c8 < c_begin + 8; ++c8) {   // tail chunks of the K dimension (at most 8 per tile)
+                    float z[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) z[q] = 0.0f;
+                    if (8 * c8 < p.N) rng.normals((uint32_t)(2 * c8), p.key0, p.key1, z);
+                    if (8 * c8 + 4 < p.N) rng.normals((uint32_t)(2 * c8 + 1), p.key0, p.key1, z + 4);
+                    float zmax_unused = 0.0f;   // the constant column must not enter max|z|
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (8 * c8 + q < p.N) zmax = fmaxf(zmax, fabsf(z[q]));
+                        if (8 * c8 + q == p.N) z[q] = 1.0f;
+                        if (8 * c8 + q > p.N) z[q] = 0.0f;
+                    }
+                    store_chunk(z, c8 - c_begin, zhi_row, zlo_row, r7s, zmax_unused);
+                }
+                fence_async_smem();                      // generic-proxy smem writes -> visible to the tensor core
+                if (kb == 0) tc_fence_before();          // this tile's first MMA overwrites a TMEM region we read earlier
+                named_bar_arrive(1 + 2 * g + slot, 160);  // hand the K-block to the MMA warp (no wait)
+            }
+            if (n > 0) epilogue(n - 1, prev_i, prev_zmax);   // tile n-1 finished long ago: no stall in steady state
+            prev_i = i;
+            prev_zmax = zmax;
         }
+        if (my_tiles > 0) epilogue(my_tiles - 1, prev_i, prev_zmax);
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         sum_s = __reduce_add_sync(0xffffffffu, sum_s);
         if (lane == 0) { s_cnt[warp] = cnt; s_sum[warp] = sum_s; }
@@ -378,7 +421,7 @@ static void tc_build_image(const double* A, const double* c, int N, uint8_t* ima
 }
 
 template <int NOUT, int KB, int GROUPS>
-static size_t tc_smem_bytes() { return 2 * (size_t)GROUPS * KB * tc::TILE_M * 128 + 2 * (size_t)KB * NOUT * 128 + 1024; }
+static size_t tc_smem_bytes() { return 2 * (size_t)GROUPS * 2 * tc::TILE_M * 128 + 2 * (size_t)KB * NOUT * 128 + 1024; }
 
 template <int NOUT, int KB, int GROUPS>
 static cudaError_t tc_prepare() {
@@ -413,7 +456,7 @@ static cudaError_t tc_occupancy_impl(int* bps) {
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
     constexpr int threads = 128 * GROUPS + 32;
-    constexpr uint32_t group_cols = (NOUT + 31) & ~31, need = group_cols * GROUPS;
+    constexpr uint32_t group_cols = (NOUT + 31) & ~31, need = 2 * group_cols * GROUPS;
     constexpr int tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
     const size_t per_cta = tc_smem_bytes<NOUT, KB, GROUPS>() + fa.sharedSizeBytes + 1024;  // + driver reservation
     int n = (int)(smem_sm / per_cta);
@@ -444,9 +487,9 @@ static TcVariant tc_variant() {
 // smallest instantiation with nout >= N and 64 * kb >= N + 1
 static const TcVariant* tc_find(int N) {
     static const TcVariant table[] = {
-        tc_variant<16, 1, MCR_TC_GROUPS_KB1>(), tc_variant<32, 1, MCR_TC_GROUPS_KB1>(), tc_variant<48, 1, MCR_TC_GROUPS_KB1>(),
-        tc_variant<64, 1, MCR_TC_GROUPS_KB1>(), tc_variant<64, 2, 2>(),
-        tc_variant<80, 2, 2>(), tc_variant<96, 2, 2>(), tc_variant<112, 2, 2>(), tc_variant<128, 2, 2>(), tc_variant<128, 3, 1>(),
+        tc_variant<16, 1, MCR_TC_GROUPS>(), tc_variant<32, 1, MCR_TC_GROUPS>(), tc_variant<48, 1, MCR_TC_GROUPS>(),
+        tc_variant<64, 1, MCR_TC_GROUPS>(), tc_variant<64, 2, MCR_TC_GROUPS>(), tc_variant<80, 2, (MCR_TC_GROUPS < 2 ? MCR_TC_GROUPS : 2)>(),
+        tc_variant<96, 2, (MCR_TC_GROUPS < 2 ? MCR_TC_GROUPS : 2)>(), tc_variant<112, 2, 2>(), tc_variant<128, 2, 2>(), tc_variant<128, 3, 2>(),
     };
     for (const TcVariant& v : table)
         if (v.nout >= N && 64 * v.kb >= N + 1) return &v;
