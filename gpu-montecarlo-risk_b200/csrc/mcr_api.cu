@@ -155,6 +155,9 @@ int mcr_create(int device, mcr_engine** out) {
     ok(cudaMalloc(&e->d_accum, sizeof(unsigned long long) * 2));
     ok(cudaMalloc(&e->d_block_partials, sizeof(uint64_t) * 2 * MAX_GRID));
     ok(cudaMalloc(&e->d_partials, sizeof(uint64_t) * MCR_PARTIAL_WORDS));
+    ok(cudaMalloc(&e->d_port_acc, sizeof(double) * 4));
+    ok(cudaMalloc(&e->d_port_hist, sizeof(unsigned long long) * MCR_PORTFOLIO_BINS));
+    ok(cudaMalloc(&e->d_port_hist_sum, sizeof(double) * MCR_PORTFOLIO_BINS));
     ok(cudaMallocHost(&e->h_partials, sizeof(uint64_t) * MCR_PARTIAL_WORDS));
     if (err != cudaSuccess) {
         mcr_destroy(e);
@@ -171,6 +174,7 @@ int mcr_destroy(mcr_engine* e) {
     cudaFree(e->d_mu); cudaFree(e->d_Acm); cudaFree(e->d_tc_image);
     cudaFree(e->d_flag_list); cudaFree(e->d_flag_count); cudaFree(e->d_accum);
     cudaFree(e->d_block_partials); cudaFree(e->d_partials);
+    cudaFree(e->d_port_acc); cudaFree(e->d_port_hist); cudaFree(e->d_port_hist_sum);
     if (e->h_partials) cudaFreeHost(e->h_partials);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -248,6 +252,8 @@ struct RunPlan {
     int variant;      // FFMA variant index or -1
     int NT;
     bool recheck;
+    bool portfolio;   // accumulator row N carries the portfolio return (tensor kernel only)
+    int rows;         // accumulator rows needed: N (+1 with the portfolio row)
 };
 
 static int auto_tc_min_n() {
@@ -261,11 +267,20 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
     plan->variant = -1;
     plan->NT = e->N;
     if (want == MCR_KERNEL_EXACT) { plan->kernel = MCR_KERNEL_EXACT; return 0; }
-    const bool tc_ok = !normals && tc_supported(e->N);
+    plan->portfolio = opt && opt->want_portfolio;
+    plan->rows = e->N + (plan->portfolio ? 1 : 0);
+    const bool tc_ok = !normals && tc_supported(plan->rows);
+    if (plan->portfolio) {
+        if (want != MCR_KERNEL_AUTO && want != MCR_KERNEL_TENSOR) return fail("portfolio outputs are produced by the tensor-core kernel only");
+        if (normals) return fail("portfolio outputs are not available with supplied normals");
+        if (!tc_ok) return fail("portfolio outputs need N <= %d (N=%d)", tc_max_n() - 1, e->N);
+        plan->kernel = MCR_KERNEL_TENSOR; plan->NT = tc_padded_n(plan->rows);
+        return 0;
+    }
     if (want == MCR_KERNEL_TENSOR) {
         if (normals) return fail("the tensor-core kernel generates its normals in-kernel; use the FFMA or EXACT kernel with supplied normals");
         if (!tc_ok) return fail("tensor-core kernel covers N <= %d in this build (N=%d)", tc_max_n(), e->N);
-        plan->kernel = MCR_KERNEL_TENSOR; plan->NT = tc_padded_n(e->N);
+        plan->kernel = MCR_KERNEL_TENSOR; plan->NT = tc_padded_n(plan->rows);
         return 0;
     }
     const int v = find_variant(e->N, e->lower, normals);
@@ -274,7 +289,7 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
     // crossover on B200: N = 32 FFMA 2.3e10 vs tensor 2.1e10 sims/s, N = 40 1.6e10 vs 1.7e10
     // (profiles/r01_sweep_ffma_vs_tensor.log)
     if (want == MCR_KERNEL_AUTO && tc_ok && (e->N >= auto_tc_min_n() || v < 0)) {
-        plan->kernel = MCR_KERNEL_TENSOR; plan->NT = tc_padded_n(e->N);
+        plan->kernel = MCR_KERNEL_TENSOR; plan->NT = tc_padded_n(plan->rows);
         return 0;
     }
     if (v >= 0) {
@@ -361,7 +376,8 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
     if (plan.kernel == MCR_KERNEL_TENSOR) {
         // split, swizzled transform image (depends on x through the constant column): rebuilt only when
         // the model or x changed
-        const size_t bytes = tc_image_bytes(N);
+        const int rows = plan.rows;
+        const size_t bytes = tc_image_bytes(rows);
         if (e->tc_image_cap < bytes) {
             cudaFree(e->d_tc_image); e->d_tc_image = nullptr; e->tc_image_cap = 0;
             MCR_CUDA(cudaMalloc(&e->d_tc_image, bytes));
@@ -376,12 +392,36 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             for (int j = 0; j < N; ++j) srow += std::fabs(e->A[(size_t)i * N + j]);
             rowabs_max = std::max(rowabs_max, srow);
         }
-        if (e->tc_gen != e->gen || e->tc_x != x) {
+        // portfolio row: P = w.R = w.mu + (w^T A) z rides through the same MMAs as one more output row
+        std::vector<double> port_row;
+        if (plan.portfolio) {
+            port_row.assign(N + 1, 0.0);
+            double var = 0;
+            for (int j = 0; j < N; ++j) {
+                double vj = 0;
+                for (int i = 0; i < N; ++i) vj += e->w[i] * e->A[(size_t)i * N + j];
+                port_row[j] = vj;
+                var += vj * vj;
+            }
+            for (int i = 0; i < N; ++i) port_row[N] += e->w[i] * e->mu[i];
+            const double sd = std::sqrt(var);
+            tl.portfolio = 1;
+            tl.port_x = opt->portfolio_loss_threshold;
+            tl.hist_lo = port_row[N] - 8.0 * sd;
+            tl.hist_width = (16.0 * sd > 0 ? 16.0 * sd : 1.0) / MCR_PORTFOLIO_BINS;
+            tl.port_acc = e->d_port_acc; tl.port_hist = e->d_port_hist; tl.port_hist_sum = e->d_port_hist_sum;
+            e->port_hist_lo = tl.hist_lo; e->port_hist_hi = tl.hist_lo + tl.hist_width * MCR_PORTFOLIO_BINS;
+            MCR_CUDA(cudaMemsetAsync(e->d_port_acc, 0, sizeof(double) * 4, s));
+            MCR_CUDA(cudaMemsetAsync(e->d_port_hist, 0, sizeof(unsigned long long) * MCR_PORTFOLIO_BINS, s));
+            MCR_CUDA(cudaMemsetAsync(e->d_port_hist_sum, 0, sizeof(double) * MCR_PORTFOLIO_BINS, s));
+        }
+        const uint64_t image_key = e->gen * 2 + (plan.portfolio ? 1 : 0);
+        if (e->tc_gen != image_key || e->tc_x != x || plan.portfolio) {
             e->tc_host_image.resize(bytes);
-            tc_build(N, e->A.data(), c.data(), e->tc_host_image.data());
+            tc_build(N, rows, e->A.data(), c.data(), plan.portfolio ? port_row.data() : nullptr, e->tc_host_image.data());
             MCR_CUDA(cudaStreamSynchronize(s));   // a previous run may still read the old image
             MCR_CUDA(cudaMemcpyAsync(e->d_tc_image, e->tc_host_image.data(), bytes, cudaMemcpyHostToDevice, s));
-            e->tc_gen = e->gen; e->tc_x = x;
+            e->tc_gen = image_key; e->tc_x = x;
         }
         // fp16x3: each operand is hi + lo with relative residual 2^-22 (plus fp16-subnormal rounding of tiny
         // z_lo, absolute 2^-25 per normal), the lo*lo product is dropped, and the tensor core accumulates in
@@ -393,8 +433,8 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         tl.delta_rel = plan.recheck ? round_up_to_float(band_scale * 2.0 * gamma * rowabs_max) : 0.f;
         tl.delta_abs = plan.recheck ? round_up_to_float(band_scale * 2.0 * gamma * cabs_max + 1e-30) : 0.f;
         int bps = 0;
-        MCR_CUDA(tc_occupancy(N, &bps));
-        if (bps < 1) return fail("tensor-core kernel for N=%d cannot be resident", N);
+        MCR_CUDA(tc_occupancy(plan.rows, plan.portfolio, &bps));
+        if (bps < 1) return fail("tensor-core kernel for N=%d%s does not fit one SM's shared memory", N, plan.portfolio ? " with the portfolio histogram" : "");
         if (const char* ov = getenv("MCR_TC_CTAS_PER_SM")) { if (atoi(ov) > 0) bps = atoi(ov); }  // tuning override
         tc_grid_full = std::min(e->num_sms * bps, MAX_GRID);
         tl.key0 = key0; tl.key1 = key1; tl.k = k; tl.d_image = e->d_tc_image;
@@ -422,7 +462,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             const int grid = (int)std::min<uint64_t>((uint64_t)tc_grid_full, tiles);
             const bool timed = e->n_timed < MAX_TIMED_CHUNKS;
             if (timed) MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed], s));
-            MCR_CUDA(tc_launch(N, tl, grid, s));
+            MCR_CUDA(tc_launch(N, plan.rows, tl, grid, s));
             if (timed) { MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed + 1], s)); ++e->n_timed; }
             ++launches;
             if (plan.recheck) {
@@ -460,7 +500,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         MCR_CUDA(launch_finalize(fin, s));
         ++launches;
     }
-    e->last_kernel = plan.kernel; e->last_NT = plan.NT; e->last_launches = launches;
+    e->last_kernel = plan.kernel; e->last_NT = plan.NT; e->last_launches = launches; e->last_portfolio = plan.portfolio;
     return 0;
 }
 
@@ -526,10 +566,20 @@ int mcr_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, doub
             const mcr_run_options* opt, mcr_result* out) {
     if (!e || !out) return fail("mcr_run: null argument");
     if (set_device(e)) return -1;
-    if (opt && (opt->want_hist || opt->want_portfolio)) return fail("mcr_run: extension outputs not built yet");
+    if (opt && opt->want_hist) return fail("mcr_run: want_hist is not built yet (use S_values)");
     MCR_CUDA(cudaEventRecord(e->ev0, e->stream));
     if (enqueue_run(e, M, path_offset, seed, x, k, opt, nullptr, e->d_partials, e->stream)) return -1;
-    return finish_sync(e, out);
+    const int rc = finish_sync(e, out);
+    if (rc == 0 && e->last_portfolio) {
+        double acc[4];
+        MCR_CUDA(cudaMemcpy(acc, e->d_port_acc, sizeof(acc), cudaMemcpyDeviceToHost));
+        MCR_CUDA(cudaMemcpy(out->portfolio_hist, e->d_port_hist, sizeof(uint64_t) * MCR_PORTFOLIO_BINS, cudaMemcpyDeviceToHost));
+        MCR_CUDA(cudaMemcpy(out->portfolio_hist_sum, e->d_port_hist_sum, sizeof(double) * MCR_PORTFOLIO_BINS, cudaMemcpyDeviceToHost));
+        out->portfolio_hits = (uint64_t)(acc[0] + 0.5);
+        out->portfolio_sum = acc[1]; out->portfolio_sumsq = acc[2]; out->portfolio_tail_loss_sum = acc[3];
+        out->portfolio_hist_lo = e->port_hist_lo; out->portfolio_hist_hi = e->port_hist_hi;
+    }
+    return rc;
 }
 
 int mcr_run_with_normals_device(mcr_engine* e, uint64_t M, const double* d_Z, double x, int k,
@@ -584,6 +634,33 @@ int mcr_dump_normals(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t s
     if (!rc && U_host && cudaMemcpy(U_host, dU, sizeof(uint32_t) * M * nb * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("D2H failed");
     cudaFree(dZ); cudaFree(dU);
     return rc;
+}
+
+int mcr_portfolio_var_es(const mcr_result* r, double alpha, double* var_out, double* es_out) {
+    if (!r || !var_out || !es_out) return fail("mcr_portfolio_var_es: null argument");
+    if (!(alpha > 0.0 && alpha < 1.0)) return fail("mcr_portfolio_var_es: alpha must be in (0, 1)");
+    uint64_t total = 0;
+    for (int b = 0; b < MCR_PORTFOLIO_BINS; ++b) total += r->portfolio_hist[b];
+    if (total == 0) return fail("mcr_portfolio_var_es: the result carries no portfolio histogram (run with want_portfolio)");
+    // walk up from the lowest returns until (1 - alpha) of the trials are covered
+    const double target = (1.0 - alpha) * (double)total;
+    const double width = (r->portfolio_hist_hi - r->portfolio_hist_lo) / MCR_PORTFOLIO_BINS;
+    double cum = 0, tail_sum = 0;
+    for (int b = 0; b < MCR_PORTFOLIO_BINS; ++b) {
+        const double c = (double)r->portfolio_hist[b];
+        if (cum + c >= target && c > 0) {
+            const double f = (target - cum) / c;   // fraction of this bin inside the tail
+            const double p_var = r->portfolio_hist_lo + width * (b + f);
+            // within the bin take the proportional share of its return sum
+            tail_sum += f * r->portfolio_hist_sum[b];
+            *var_out = -p_var;
+            *es_out = target > 0 ? -(tail_sum / target) : -p_var;
+            return 0;
+        }
+        cum += c;
+        tail_sum += r->portfolio_hist_sum[b];
+    }
+    return fail("mcr_portfolio_var_es: histogram exhausted");
 }
 
 int mcr_measure_fp32_peak(mcr_engine* e, float ms_target, double* tflops_out) {

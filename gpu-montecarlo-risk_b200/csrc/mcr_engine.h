@@ -50,6 +50,12 @@ struct mcr_engine {
     uint64_t* d_block_partials = nullptr;
     uint64_t* d_partials = nullptr;
     uint64_t* h_partials = nullptr;  // pinned
+    // portfolio extension accumulators (device)
+    double* d_port_acc = nullptr;
+    unsigned long long* d_port_hist = nullptr;
+    double* d_port_hist_sum = nullptr;
+    double port_hist_lo = 0, port_hist_hi = 0;
+    bool last_portfolio = false;
     // last async run bookkeeping
     int last_kernel = 0, last_NT = 0, last_launches = 0;
 };

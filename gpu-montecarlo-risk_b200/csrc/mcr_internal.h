@@ -95,15 +95,23 @@ struct TcLaunch {
     uint32_t* flag_count;
     uint32_t flag_cap;
     uint64_t* block_partials;
+    // portfolio extension
+    int32_t portfolio;
+    double port_x, hist_lo, hist_width;
+    double* port_acc;
+    unsigned long long* port_hist;
+    double* port_hist_sum;
 };
 int tc_max_n();
-bool tc_supported(int N);
-size_t tc_image_bytes(int N);
-int tc_padded_n(int N);
-// A: N x N row-major fp64 transform, c: N thresholds mu_i + x  ->  host image (tc_image_bytes)
-void tc_build(int N, const double* A, const double* c, uint8_t* image);
-cudaError_t tc_occupancy(int N, int* blocks_per_sm);
-cudaError_t tc_launch(int N, const TcLaunch& l, int grid, cudaStream_t s);
+// `rows` = accumulator rows needed: N, or N + 1 when the last row carries the portfolio return
+bool tc_supported(int rows);
+size_t tc_image_bytes(int rows);
+int tc_padded_n(int rows);
+// A: N x N row-major fp64 transform, c: N thresholds mu_i + x, port_row: nullptr or N + 1 values
+// (w^T A, then w.mu)  ->  host image (tc_image_bytes(rows))
+void tc_build(int N, int rows, const double* A, const double* c, const double* port_row, uint8_t* image);
+cudaError_t tc_occupancy(int rows, bool portfolio, int* blocks_per_sm);
+cudaError_t tc_launch(int N, int rows, const TcLaunch& l, int grid, cudaStream_t s);
 
 cudaError_t launch_dump(uint64_t M, uint64_t path_offset, uint32_t key0, uint32_t key1, int N,
                         float* dZ, uint32_t* dU, cudaStream_t s);

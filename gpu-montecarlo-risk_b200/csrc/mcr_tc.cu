@@ -18,6 +18,7 @@
 // the guard band is about as narrow as the fp32 FFMA kernel's and the final counts remain
 // bit-identical to fp64 on the same normals.  (bf16x3 was tried first: 2^-16, four times as many
 // trials sent to the fp64 fix-up.)
+#include "../../include/mcr_b200.h"
 #include "mcr_internal.h"
 #include "mcr_rng.cuh"
 
@@ -120,6 +121,7 @@ __host__ __device__ inline uint32_t operand_offset(int rows, int r, int k) {
 }  // namespace tc
 
 constexpr double TC_SCALE = 1024.0;  // 2^10, see tc_build_image
+constexpr uint32_t PORT_BINS = MCR_PORTFOLIO_BINS;
 
 struct TcParams {
     uint64_t M, path_offset;
@@ -132,6 +134,13 @@ struct TcParams {
     uint32_t* flag_count;
     uint32_t flag_cap;
     uint64_t* block_partials;
+    // portfolio extension (north-star A7; no reference code): accumulator column NOUT-1 holds w.R
+    int32_t portfolio;            // 0 = off (column NOUT-1 is an ordinary padded / asset row)
+    float port_thresh;            // scaled: tail event is  D < port_thresh  (= -x_p * TC_SCALE)
+    float hist_lo, hist_inv_w;    // unscaled histogram origin and 1 / bin width
+    double* port_acc;             // [4] += hits, sum P, sum P^2, sum of -P over tail events
+    unsigned long long* port_hist;  // [MCR_PORTFOLIO_BINS] counts
+    double* port_hist_sum;          // [MCR_PORTFOLIO_BINS] per-bin sum of P
 };
 
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -208,7 +217,10 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
     uint8_t* s_ring = smem;                                   // [group][slot][hi|lo][128 x 128 B]
     uint8_t* s_bhi = smem + 2 * GROUPS * SLOT_BYTES;
     uint8_t* s_blo = s_bhi + B_BYTES;
+    uint32_t* s_hist_cnt = reinterpret_cast<uint32_t*>(s_blo + B_BYTES);          // only when p.portfolio (host sizes smem)
+    float* s_hist_sum = reinterpret_cast<float*>(s_hist_cnt + PORT_BINS);
     __shared__ uint64_t s_empty[GROUPS][2], s_done[GROUPS][2];
+    __shared__ double s_port[4 * GROUPS][4];
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_cnt[4 * GROUPS], s_sum[4 * GROUPS];
 
@@ -220,6 +232,8 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
         uint4* dst = reinterpret_cast<uint4*>(s_bhi);
         for (uint32_t t = tid; t < 2 * B_BYTES / 16; t += NTHREADS) dst[t] = src[t];
     }
+    if (p.portfolio)
+        for (uint32_t t = tid; t < PORT_BINS; t += NTHREADS) { s_hist_cnt[t] = 0u; s_hist_sum[t] = 0.0f; }
     if (tid == 0)
         for (int gg = 0; gg < GROUPS; ++gg)
             for (int b = 0; b < 2; ++b) { mbar_init(&s_empty[gg][b], 1); mbar_init(&s_done[gg][b], 1); }
@@ -235,6 +249,8 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
     const uint64_t cta_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     constexpr uint32_t IDESC = make_idesc(NOUT);
     uint32_t cnt = 0, sum_s = 0;
+    uint32_t p_hits = 0;
+    float p_sum = 0.f, p_sum2 = 0.f, p_tail = 0.f;
 
     if (warp == MMA_WARP) {
         // ---- MMA warp: K-block u of group g, round-robin over g, in the order the groups produce them ----
@@ -303,9 +319,27 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    if (c0 + c < NOUT) {
+                    if (c0 + c < NOUT - 1) {
                         S += v[c] >> 31;
                         band = fminf(band, fabsf(__uint_as_float(v[c])));
+                    } else if (c0 + c == NOUT - 1) {
+                        if (!p.portfolio) {
+                            S += v[c] >> 31;
+                            band = fminf(band, fabsf(__uint_as_float(v[c])));
+                        } else if (i < p.M) {
+                            // portfolio return of this trial (the host put w^T A and w.mu in row NOUT-1)
+                            const float Ps = __uint_as_float(v[c]);
+                            const float P = Ps * (float)(1.0 / TC_SCALE);
+                            const bool tail = Ps < p.port_thresh;
+                            p_hits += tail ? 1u : 0u;
+                            p_tail += tail ? -P : 0.0f;
+                            p_sum += P;
+                            p_sum2 = fmaf(P, P, p_sum2);
+                            int bin = (int)floorf((P - p.hist_lo) * p.hist_inv_w);
+                            bin = bin < 0 ? 0 : (bin >= (int)PORT_BINS ? (int)PORT_BINS - 1 : bin);
+                            atomicAdd(&s_hist_cnt[bin], 1u);
+                            atomicAdd(&s_hist_sum[bin], P);
+                        }
                     }
                 }
             }
@@ -383,6 +417,14 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         sum_s = __reduce_add_sync(0xffffffffu, sum_s);
         if (lane == 0) { s_cnt[warp] = cnt; s_sum[warp] = sum_s; }
+        if (p.portfolio) {
+            double d[4] = {(double)p_hits, (double)p_sum, (double)p_sum2, (double)p_tail};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                for (int o = 16; o > 0; o >>= 1) d[q] += __shfl_down_sync(0xffffffffu, d[q], o);
+            if (lane == 0)
+                for (int q = 0; q < 4; ++q) s_port[warp][q] = d[q];
+        }
     }
 
     // ---- block reduction + teardown ----
@@ -394,6 +436,20 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
         p.block_partials[2 * (uint64_t)blockIdx.x] = c;
         p.block_partials[2 * (uint64_t)blockIdx.x + 1] = s;
     }
+    if (p.portfolio) {
+        if (tid < 4) {
+            double a = 0;
+            for (int w = 0; w < 4 * GROUPS; ++w) a += s_port[w][tid];
+            atomicAdd(&p.port_acc[tid], a);
+        }
+        for (uint32_t t = tid; t < PORT_BINS; t += NTHREADS) {
+            const uint32_t c = s_hist_cnt[t];
+            if (c) {
+                atomicAdd(&p.port_hist[t], (unsigned long long)c);
+                atomicAdd(&p.port_hist_sum[t], (double)s_hist_sum[t]);
+            }
+        }
+    }
     if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
@@ -403,13 +459,14 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
 // fp16 hi + lo.  The 2^10 scale only moves the values (|A| ~ 1e-2, lo parts ~ 1e-6) out of fp16's
 // subnormal range; signs and the (equally scaled) guard band are unaffected.
 template <int NOUT, int KB>
-static void tc_build_image(const double* A, const double* c, int N, uint8_t* image) {
+static void tc_build_image(const double* A, const double* c, int N, const double* port_row, uint8_t* image) {
     const size_t bytes = (size_t)KB * NOUT * 128;
     memset(image, 0, 2 * bytes);
     for (int i = 0; i < NOUT; ++i)
         for (int k = 0; k <= N; ++k) {
             double v;
-            if (k < N) v = (i < N) ? A[(size_t)i * N + k] : 0.0;
+            if (port_row && i == NOUT - 1) v = port_row[k];   // portfolio: w^T A (k < N) and w.mu (k = N)
+            else if (k < N) v = (i < N) ? A[(size_t)i * N + k] : 0.0;
             else v = (i < N) ? c[i] : 1.0;
             v *= TC_SCALE;
             const __half hi = __float2half_rn((float)v);
@@ -421,23 +478,25 @@ static void tc_build_image(const double* A, const double* c, int N, uint8_t* ima
 }
 
 template <int NOUT, int KB, int GROUPS>
-static size_t tc_smem_bytes() { return 2 * (size_t)GROUPS * 2 * tc::TILE_M * 128 + 2 * (size_t)KB * NOUT * 128 + 1024; }
+static size_t tc_smem_bytes(bool portfolio) {
+    return 2 * (size_t)GROUPS * 2 * tc::TILE_M * 128 + 2 * (size_t)KB * NOUT * 128 + 1024 + (portfolio ? 8 * (size_t)PORT_BINS : 0);
+}
 
 template <int NOUT, int KB, int GROUPS>
-static cudaError_t tc_prepare() {
+static cudaError_t tc_prepare(bool portfolio) {
     // opt in to the large dynamic shared memory and the largest carveout (several CTAs per SM overlap
     // each other's bubbles); both are per-device function attributes, cheap to set repeatedly
     cudaError_t e = cudaFuncSetAttribute(tc_path_kernel<NOUT, KB, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)tc_smem_bytes<NOUT, KB, GROUPS>());
+                                         (int)tc_smem_bytes<NOUT, KB, GROUPS>(portfolio));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(tc_path_kernel<NOUT, KB, GROUPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 template <int NOUT, int KB, int GROUPS>
 static cudaError_t tc_launch_impl(const TcParams& p, int grid, cudaStream_t s) {
-    cudaError_t e = tc_prepare<NOUT, KB, GROUPS>();
+    cudaError_t e = tc_prepare<NOUT, KB, GROUPS>(p.portfolio != 0);
     if (e != cudaSuccess) return e;
-    tc_path_kernel<NOUT, KB, GROUPS><<<grid, 128 * GROUPS + 32, tc_smem_bytes<NOUT, KB, GROUPS>(), s>>>(p);
+    tc_path_kernel<NOUT, KB, GROUPS><<<grid, 128 * GROUPS + 32, tc_smem_bytes<NOUT, KB, GROUPS>(p.portfolio != 0), s>>>(p);
     return cudaGetLastError();
 }
 
@@ -445,8 +504,9 @@ static cudaError_t tc_launch_impl(const TcParams& p, int grid, cudaStream_t s) {
 // for this kernel although the hardware co-schedules more (measured: 4 CTAs/SM run 2.2x faster than 1):
 // shared memory, TMEM columns (512 per SM), threads and registers bound it.
 template <int NOUT, int KB, int GROUPS>
-static cudaError_t tc_occupancy_impl(int* bps) {
-    cudaError_t e = tc_prepare<NOUT, KB, GROUPS>();
+static cudaError_t tc_occupancy_impl(int* bps, bool portfolio) {
+    if (tc_smem_bytes<NOUT, KB, GROUPS>(portfolio) > 227 * 1024) { *bps = 0; return cudaSuccess; }
+    cudaError_t e = tc_prepare<NOUT, KB, GROUPS>(portfolio);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa{};
     e = cudaFuncGetAttributes(&fa, tc_path_kernel<NOUT, KB, GROUPS>);
@@ -458,7 +518,7 @@ static cudaError_t tc_occupancy_impl(int* bps) {
     constexpr int threads = 128 * GROUPS + 32;
     constexpr uint32_t group_cols = (NOUT + 31) & ~31, need = 2 * group_cols * GROUPS;
     constexpr int tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
-    const size_t per_cta = tc_smem_bytes<NOUT, KB, GROUPS>() + fa.sharedSizeBytes + 1024;  // + driver reservation
+    const size_t per_cta = tc_smem_bytes<NOUT, KB, GROUPS>(portfolio) + fa.sharedSizeBytes + 1024;  // + driver reservation
     int n = (int)(smem_sm / per_cta);
     n = std::min(n, 512 / tmem_cols);
     n = std::min(n, 2048 / threads);
@@ -466,16 +526,16 @@ static cudaError_t tc_occupancy_impl(int* bps) {
     *bps = std::max(n, 0);
     if (getenv("MCR_DEBUG"))
         fprintf(stderr, "[mcr] tc_path_kernel<%d,%d,%d>: %d CTAs/SM (dyn smem %zu, static %zu, regs %d, tmem cols %d)\n",
-                NOUT, KB, GROUPS, *bps, tc_smem_bytes<NOUT, KB, GROUPS>(), fa.sharedSizeBytes, fa.numRegs, tmem_cols);
+                NOUT, KB, GROUPS, *bps, tc_smem_bytes<NOUT, KB, GROUPS>(portfolio), fa.sharedSizeBytes, fa.numRegs, tmem_cols);
     return cudaSuccess;
 }
 
 struct TcVariant {
     int nout, kb, groups;
     size_t image_bytes;
-    void (*build)(const double*, const double*, int, uint8_t*);
+    void (*build)(const double*, const double*, int, const double*, uint8_t*);
     cudaError_t (*launch)(const TcParams&, int, cudaStream_t);
-    cudaError_t (*occupancy)(int*);
+    cudaError_t (*occupancy)(int*, bool);
 };
 
 template <int NOUT, int KB, int GROUPS>
@@ -498,23 +558,26 @@ static const TcVariant* tc_find(int N) {
 
 int tc_max_n() { return 128; }
 
-bool tc_supported(int N) { return tc_find(N) != nullptr; }
+bool tc_supported(int rows) { return tc_find(rows) != nullptr; }
 
-size_t tc_image_bytes(int N) { const TcVariant* v = tc_find(N); return v ? v->image_bytes : 0; }
+size_t tc_image_bytes(int rows) { const TcVariant* v = tc_find(rows); return v ? v->image_bytes : 0; }
 
-int tc_padded_n(int N) { const TcVariant* v = tc_find(N); return v ? v->nout : 0; }
+int tc_padded_n(int rows) { const TcVariant* v = tc_find(rows); return v ? v->nout : 0; }
 
-void tc_build(int N, const double* A, const double* c, uint8_t* image) { tc_find(N)->build(A, c, N, image); }
+void tc_build(int N, int rows, const double* A, const double* c, const double* port_row, uint8_t* image) { tc_find(rows)->build(A, c, N, port_row, image); }
 
-cudaError_t tc_occupancy(int N, int* bps) { return tc_find(N)->occupancy(bps); }
+cudaError_t tc_occupancy(int rows, bool portfolio, int* bps) { return tc_find(rows)->occupancy(bps, portfolio); }
 
-cudaError_t tc_launch(int N, const TcLaunch& l, int grid, cudaStream_t s) {
+cudaError_t tc_launch(int N, int rows, const TcLaunch& l, int grid, cudaStream_t s) {
     TcParams p{};
     p.M = l.M; p.path_offset = l.path_offset; p.key0 = l.key0; p.key1 = l.key1; p.k = l.k; p.N = N;
     p.delta_rel = (float)(l.delta_rel * TC_SCALE); p.delta_abs = (float)(l.delta_abs * TC_SCALE);  // accumulators are scaled
     p.B_image = reinterpret_cast<const uint4*>(l.d_image); p.S_out = l.S_out;
     p.flag_list = l.flag_list; p.flag_count = l.flag_count; p.flag_cap = l.flag_cap; p.block_partials = l.block_partials;
-    return tc_find(N)->launch(p, grid, s);
+    p.portfolio = l.portfolio; p.port_thresh = (float)(-l.port_x * TC_SCALE);
+    p.hist_lo = (float)l.hist_lo; p.hist_inv_w = (float)(1.0 / l.hist_width);
+    p.port_acc = l.port_acc; p.port_hist = l.port_hist; p.port_hist_sum = l.port_hist_sum;
+    return tc_find(rows)->launch(p, grid, s);
 }
 
 }  // namespace mcr

@@ -99,6 +99,7 @@ PROTOTYPES = {
                                               C.POINTER(RunOptions), C.POINTER(Result)]),
     "mcr_dump_normals": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mcr_simulate_host": (C.c_int, [C.POINTER(HostRequest), C.POINTER(Result)]),
+    "mcr_portfolio_var_es": (C.c_int, [C.POINTER(Result), C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mcr_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_float, C.POINTER(C.c_double)]),
 }
 

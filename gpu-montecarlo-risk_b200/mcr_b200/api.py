@@ -44,6 +44,7 @@ class RunResult:
     padded_N: int
     launches: int
     S_values: np.ndarray = None
+    portfolio: dict = None   # extension outputs of a want_portfolio run (see Engine.run)
 
     @staticmethod
     def from_c(r: Result, S_values=None):
@@ -52,13 +53,30 @@ class RunResult:
                          int(r.padded_N), int(r.launches), S_values)
 
 
-def make_options(kernel=KERNEL_AUTO, no_recheck=False, d_S_values=0) -> RunOptions:
+def make_options(kernel=KERNEL_AUTO, no_recheck=False, d_S_values=0, portfolio_threshold=None) -> RunOptions:
     o = RunOptions()
     o.struct_size = C.sizeof(RunOptions)
     o.kernel = int(kernel)
     o.no_recheck = int(bool(no_recheck))
     o.d_S_values = d_S_values or None
+    if portfolio_threshold is not None:
+        o.want_portfolio = 1
+        o.portfolio_loss_threshold = float(portfolio_threshold)
     return o
+
+
+def portfolio_outputs(r: Result, alphas=(0.95, 0.99)) -> dict:
+    """Extension outputs (north-star A7): moments, tail-event count, and VaR / ES of the loss -w.R."""
+    n = int(r.n_paths)
+    out = {"hits": int(r.portfolio_hits), "mean": r.portfolio_sum / n, "tail_loss_sum": r.portfolio_tail_loss_sum,
+           "var": r.portfolio_sumsq / n - (r.portfolio_sum / n) ** 2,
+           "hist": np.ctypeslib.as_array(r.portfolio_hist).copy(), "hist_sum": np.ctypeslib.as_array(r.portfolio_hist_sum).copy(),
+           "hist_lo": r.portfolio_hist_lo, "hist_hi": r.portfolio_hist_hi, "VaR": {}, "ES": {}}
+    for a in alphas:
+        v, e = C.c_double(), C.c_double()
+        check(_lib.load().mcr_portfolio_var_es(C.byref(r), float(a), C.byref(v), C.byref(e)))
+        out["VaR"][a], out["ES"][a] = v.value, e.value
+    return out
 
 
 class Engine:
@@ -94,11 +112,20 @@ class Engine:
         self.upload_model(mu, A, a_is_lower=(mode == TRANSFORM_LOWER))
         return A
 
-    def run(self, M, seed, x, k, path_offset=0, kernel=KERNEL_AUTO, no_recheck=False) -> RunResult:
+    def run(self, M, seed, x, k, path_offset=0, kernel=KERNEL_AUTO, no_recheck=False, portfolio_threshold=None,
+            weights=None) -> RunResult:
+        """portfolio_threshold=x_p additionally reduces the portfolio return w.R (weights default 1/N):
+        result.portfolio = {hits = #{w.R < -x_p}, mean, var, tail_loss_sum, hist..., VaR{alpha}, ES{alpha}}."""
         r = Result()
-        o = make_options(kernel, no_recheck)
+        o = make_options(kernel, no_recheck, portfolio_threshold=portfolio_threshold)
+        if weights is not None:
+            w = _f64(weights)
+            check(self._lib.mcr_set_portfolio_weights(self._h, w.ctypes.data, w.shape[0]))
         check(self._lib.mcr_run(self._h, int(M), int(path_offset), int(seed), float(x), int(k), C.byref(o), C.byref(r)))
-        return RunResult.from_c(r)
+        res = RunResult.from_c(r)
+        if portfolio_threshold is not None:
+            res.portfolio = portfolio_outputs(r)
+        return res
 
     def run_async(self, M, seed, x, k, d_partials_ptr, stream_ptr, path_offset=0, kernel=KERNEL_AUTO,
                   no_recheck=False, d_S_values=0):

@@ -158,6 +158,11 @@ typedef struct mcr_host_request {
 } mcr_host_request;
 int mcr_simulate_host(const mcr_host_request *req, mcr_result *out);
 
+/* Extension (north-star A7, no reference counterpart): value-at-risk and expected shortfall of the portfolio
+ * loss -w.R at confidence alpha (e.g. 0.99), from the merged histogram of a want_portfolio run.  VaR is exact
+ * to one bin width ((hist_hi - hist_lo) / MCR_PORTFOLIO_BINS = sigma_p / 128); ES uses the exact per-bin sums. */
+int mcr_portfolio_var_es(const mcr_result *r, double alpha, double *var_out, double *es_out);
+
 /* FP32-pipe calibration used by bench.py for the roofline denominator: runs a pure FFMA2 kernel
  * (no memory traffic) for about `ms_target` ms and reports achieved fp32 TFLOP/s. */
 int mcr_measure_fp32_peak(mcr_engine *e, float ms_target, double *tflops_out);

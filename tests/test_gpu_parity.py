@@ -235,6 +235,40 @@ def test_tensor_kernel_raw_decisions_are_close_and_recheck_makes_them_exact(engi
         assert 0 < fix.n_rechecked < M // 50
 
 
+def test_portfolio_extension_against_oracle(engine, oracle):
+    """North-star extension (A7; the reference has no portfolio / VaR / ES code, so this is checked
+    against the oracle's own definition on the dumped normals): P = w.R per trial, hits = #{P < -x_p},
+    mean/variance, ES numerator, VaR/ES from the merged 2048-bin histogram.
+    Stated tolerances: moments 1e-5 relative (fp16x3 products, fp32 per-thread partial sums);
+    hits may differ by the trials whose P sits within 1e-6 of the threshold; VaR within one
+    histogram bin (sigma_p / 128); ES within 0.2 % (bin interpolation at the VaR boundary)."""
+    for N, weights in ((15, None), (50, None), (100, "ramp")):
+        mu, Sigma, x, k = model(N)
+        A = engine.upload_sigma(mu, Sigma)
+        w = np.full(N, 1.0 / N) if weights is None else np.arange(1, N + 1) / np.arange(1, N + 1).sum()
+        M, seed, xp = 1000000, 2025, 0.015
+        r = engine.run(M, seed, x, k, portfolio_threshold=xp, weights=w)
+        assert r.kernel == "tensor"
+        Z, _ = engine.dump_normals(M, seed)
+        ro = oracle.run_normals(A, mu, k, x, Z)
+        assert (r.count, r.sum_S) == (ro["count"], ro["sum_S"])       # the base outputs are untouched and exact
+        P = oracle.portfolio(A, mu, w, Z)
+        pf = r.portfolio
+        near = int((np.abs(P + xp) < 1e-6).sum())
+        assert abs(pf["hits"] - int((P < -xp).sum())) <= near + 1
+        assert pf["mean"] == pytest.approx(P.mean(), rel=1e-4, abs=1e-8)
+        assert pf["var"] == pytest.approx(P.var(), rel=1e-4)
+        assert pf["tail_loss_sum"] == pytest.approx(-P[P < -xp].sum(), rel=1e-4, abs=1e-6)
+        assert int(pf["hist"].sum()) == M
+        width = (pf["hist_hi"] - pf["hist_lo"]) / len(pf["hist"])
+        for a in (0.95, 0.99):
+            q = np.quantile(-P, a)                                    # VaR_a of the loss
+            es = (-P)[-P >= q].mean()
+            assert abs(pf["VaR"][a] - q) <= width
+            assert pf["ES"][a] == pytest.approx(es, rel=2e-3)
+        engine.run(1000, seed, x, k, weights=np.full(N, 1.0 / N))      # restore default weights
+
+
 def test_kernel_selection(engine):
     mu, Sigma, x, k = model(15)
     engine.upload_sigma(mu, Sigma)
