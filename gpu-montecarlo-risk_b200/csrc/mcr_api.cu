@@ -171,7 +171,7 @@ int mcr_destroy(mcr_engine* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->d_mu); cudaFree(e->d_Acm); cudaFree(e->d_tc_image);
+    cudaFree(e->d_mu); cudaFree(e->d_Acm); cudaFree(e->d_tc_image); cudaFree(e->d_slab_image); cudaFree(e->d_S_acc);
     cudaFree(e->d_flag_list); cudaFree(e->d_flag_count); cudaFree(e->d_accum);
     cudaFree(e->d_block_partials); cudaFree(e->d_partials);
     cudaFree(e->d_port_acc); cudaFree(e->d_port_hist); cudaFree(e->d_port_hist_sum);
@@ -253,6 +253,7 @@ struct RunPlan {
     int NT;
     bool recheck;
     bool portfolio;   // accumulator row N carries the portfolio return (tensor kernel only)
+    bool slab;        // N > 128: tensor kernel over row slabs of 128 assets
     int rows;         // accumulator rows needed: N (+1 with the portfolio row)
 };
 
@@ -263,12 +264,19 @@ static int auto_tc_min_n() {
 
 static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool normals, RunPlan* plan) {
     const int want = opt ? opt->kernel : MCR_KERNEL_AUTO;
+    *plan = RunPlan{};
     plan->recheck = !(opt && opt->no_recheck);
     plan->variant = -1;
     plan->NT = e->N;
+    plan->rows = e->N;
     if (want == MCR_KERNEL_EXACT) { plan->kernel = MCR_KERNEL_EXACT; return 0; }
     plan->portfolio = opt && opt->want_portfolio;
+    plan->slab = false;
     plan->rows = e->N + (plan->portfolio ? 1 : 0);
+    if (!normals && !plan->portfolio && e->N > tc_max_n() && (want == MCR_KERNEL_AUTO || want == MCR_KERNEL_TENSOR)) {
+        plan->kernel = MCR_KERNEL_TENSOR; plan->slab = true; plan->NT = 128 * slab_count(e->N);
+        return 0;
+    }
     const bool tc_ok = !normals && tc_supported(plan->rows);
     if (plan->portfolio) {
         if (want != MCR_KERNEL_AUTO && want != MCR_KERNEL_TENSOR) return fail("portfolio outputs are produced by the tensor-core kernel only");
@@ -373,7 +381,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
 
     TcLaunch tl{};
     int tc_grid_full = 0;
-    if (plan.kernel == MCR_KERNEL_TENSOR) {
+    if (plan.kernel == MCR_KERNEL_TENSOR && !plan.slab) {
         // split, swizzled transform image (depends on x through the constant column): rebuilt only when
         // the model or x changed
         const int rows = plan.rows;
@@ -442,8 +450,48 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         tl.block_partials = e->d_block_partials;
     }
 
-    for (uint64_t done = 0; done < M || (M == 0 && done == 0); done += CHUNK_PATHS) {
-        const uint64_t m = std::min<uint64_t>(CHUNK_PATHS, M - done);
+    // ---- row-slab tensor path (N > 128): per-slab images, per-trial uint16 accumulator ----
+    const uint64_t chunk_paths = plan.slab ? SLAB_CHUNK_PATHS : CHUNK_PATHS;
+    std::vector<double> slab_drel, slab_dabs;
+    if (plan.slab) {
+        const int ns = slab_count(N);
+        const size_t bytes = slab_image_bytes(N, e->lower);
+        if (e->slab_image_cap < bytes) {
+            cudaFree(e->d_slab_image); e->d_slab_image = nullptr; e->slab_image_cap = 0;
+            MCR_CUDA(cudaMalloc(&e->d_slab_image, bytes));
+            e->slab_image_cap = bytes; e->slab_gen = 0;
+        }
+        if (!e->d_S_acc) MCR_CUDA(cudaMalloc(&e->d_S_acc, sizeof(uint16_t) * SLAB_CHUNK_PATHS));
+        std::vector<double> c(N);
+        for (int i = 0; i < N; ++i) c[i] = e->mu[i] + x;
+        if (e->slab_gen != e->gen || e->slab_x != x) {
+            e->slab_host_image.resize(bytes);
+            e->slab_offsets.assign(ns + 1, 0);
+            slab_build(N, e->lower, e->A.data(), c.data(), e->slab_host_image.data(), e->slab_offsets.data());
+            MCR_CUDA(cudaStreamSynchronize(s));
+            MCR_CUDA(cudaMemcpyAsync(e->d_slab_image, e->slab_host_image.data(), bytes, cudaMemcpyHostToDevice, s));
+            e->slab_gen = e->gen; e->slab_x = x;
+        }
+        // guard band per slab: fp16x3 split (3 * 2^-22) + fp32 accumulation over 12 MMAs per K-block
+        static const double band_scale = [] { const char* v = getenv("MCR_TC_BAND_SCALE"); return v && *v ? atof(v) : 1.0; }();
+        for (int t = 0; t < ns; ++t) {
+            const int kbn = (slab_ncols(N, t, e->lower) + 1 + 63) / 64;
+            const double gamma = std::ldexp(1.0, -19) * std::max(1.0, kbn / 2.0);
+            // sum_j |a_ij||z_j| <= ||a_i||_2 ||z||_2 (Cauchy-Schwarz): the kernel tracks ||z||_2 of the trial
+            double cabs = 0, rownorm = 0;
+            for (int i = 128 * t; i < std::min(N, 128 * (t + 1)); ++i) {
+                cabs = std::max(cabs, std::fabs(c[i]));
+                double ss = 0;
+                for (int j = 0; j < N; ++j) ss += e->A[(size_t)i * N + j] * e->A[(size_t)i * N + j];
+                rownorm = std::max(rownorm, std::sqrt(ss));
+            }
+            slab_drel.push_back(plan.recheck ? band_scale * 2.0 * gamma * rownorm : 0.0);
+            slab_dabs.push_back(plan.recheck ? band_scale * 2.0 * gamma * cabs + 1e-30 : 0.0);
+        }
+    }
+
+    for (uint64_t done = 0; done < M || (M == 0 && done == 0); done += chunk_paths) {
+        const uint64_t m = std::min<uint64_t>(chunk_paths, M - done);
         if (m == 0) break;
         MCR_CUDA(cudaMemsetAsync(e->d_accum, 0, sizeof(unsigned long long) * 2, s));
         MCR_CUDA(cudaMemsetAsync(e->d_flag_count, 0, sizeof(uint32_t), s));
@@ -456,7 +504,32 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         xp.Z = dZ ? dZ + done * (uint64_t)N : nullptr;
         xp.S_out = d_S ? d_S + done : nullptr;
         xp.accum = e->d_accum;
-        if (plan.kernel == MCR_KERNEL_TENSOR) {
+        if (plan.slab) {
+            const int ns = slab_count(N);
+            for (int t = 0; t < ns; ++t) {
+                SlabLaunch sl{};
+                sl.M = m; sl.path_offset = path_offset + done; sl.key0 = key0; sl.key1 = key1;
+                sl.ncols = slab_ncols(N, t, e->lower);
+                sl.delta_rel = slab_drel[t]; sl.delta_abs = slab_dabs[t];
+                sl.d_slab_image = (const uint8_t*)e->d_slab_image + e->slab_offsets[t];
+                sl.S_acc = e->d_S_acc; sl.first_slab = t == 0;
+                const bool timed = e->n_timed < MAX_TIMED_CHUNKS;
+                if (timed) MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed], s));
+                MCR_CUDA(slab_launch(sl, e->num_sms, s));
+                if (timed) { MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed + 1], s)); ++e->n_timed; }
+                ++launches;
+            }
+            const int grid = (int)std::min<uint64_t>((uint64_t)std::min(e->num_sms * 8, MAX_GRID), (m + 255) / 256);
+            MCR_CUDA(slab_count_launch(m, e->d_S_acc, k, xp.S_out, e->d_flag_list, e->d_flag_count, FLAG_CAP, e->d_block_partials, grid, s));
+            ++launches;
+            if (plan.recheck) {
+                xp.flag_list = e->d_flag_list; xp.flag_count = e->d_flag_count; xp.flag_cap = FLAG_CAP;
+                MCR_CUDA(launch_exact(xp, e->num_sms, s));
+                ++launches;
+            }
+            fin.block_partials = e->d_block_partials; fin.n_blocks = grid;
+            fin.flag_count = e->d_flag_count; fin.flag_cap = FLAG_CAP;
+        } else if (plan.kernel == MCR_KERNEL_TENSOR) {
             tl.M = m; tl.path_offset = path_offset + done; tl.S_out = xp.S_out;
             const uint64_t tiles = (m + 127) / 128;
             const int grid = (int)std::min<uint64_t>((uint64_t)tc_grid_full, tiles);

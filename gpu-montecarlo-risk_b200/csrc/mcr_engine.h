@@ -7,6 +7,7 @@
 
 namespace mcr {
 constexpr uint64_t CHUNK_PATHS = 1ull << 27;   // trials per launch of the path kernel
+constexpr uint64_t SLAB_CHUNK_PATHS = 1ull << 24;  // trials per chunk on the row-slab path (uint16 accumulator per trial)
 constexpr uint32_t FLAG_CAP = 1u << 22;        // fix-up list entries per chunk (3.1 % of a chunk)
 constexpr int MAX_GRID = 148 * 16 * 2;
 constexpr int MAX_TIMED_CHUNKS = 16;
@@ -42,6 +43,14 @@ struct mcr_engine {
     uint64_t tc_gen = 0;
     double tc_x = 0;
     std::vector<uint8_t> tc_host_image;
+    // row-slab tensor path (N > 128)
+    void* d_slab_image = nullptr;
+    size_t slab_image_cap = 0;
+    uint64_t slab_gen = 0;
+    double slab_x = 0;
+    std::vector<uint8_t> slab_host_image;
+    std::vector<size_t> slab_offsets;
+    uint16_t* d_S_acc = nullptr;
     double gamma_rowabs_max = 0;  // max_i gamma_i * sum_j |A_ij|
     // scratch
     uint32_t* d_flag_list = nullptr;

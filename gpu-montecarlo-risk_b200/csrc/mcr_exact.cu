@@ -43,14 +43,34 @@ __global__ void __launch_bounds__(EXACT_WARPS * 32) exact_kernel(const ExactPara
         }
         __syncwarp();
         int S = 0;
-        for (int r = lane; r < p.N; r += 32) {
-            double t = 0.0;
-            const int jend = p.lower ? r + 1 : p.N;
-            for (int j = 0; j < jend; ++j)
-                t = __dadd_rn(t, __dmul_rn(z[j], p.A_cm[(size_t)j * p.N + r]));
-            double R = __dadd_rn(0.0, __dmul_rn(1.0, t));
-            R = __dadd_rn(R, p.mu[r]);
-            S += (R < neg_x) ? 1 : 0;
+        // four rows per lane at a time: each row's sum is one dependent fp64 chain (reference order), four
+        // independent chains keep the FP64 pipe busy while a chain waits on its previous add
+        for (int r0 = lane; r0 < p.N; r0 += 128) {
+            double t[4] = {0.0, 0.0, 0.0, 0.0};
+            int jend[4], jmax = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = r0 + 32 * q;
+                jend[q] = r < p.N ? (p.lower ? r + 1 : p.N) : 0;
+                jmax = jend[q] > jmax ? jend[q] : jmax;
+            }
+            const double* a = p.A_cm + r0;
+            for (int j = 0; j < jmax; ++j) {
+                const double zj = z[j];
+                const double* aj = a + (size_t)j * p.N;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (j < jend[q]) t[q] = __dadd_rn(t[q], __dmul_rn(zj, __ldg(aj + 32 * q)));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = r0 + 32 * q;
+                if (r < p.N) {
+                    double R = __dadd_rn(0.0, __dmul_rn(1.0, t[q]));
+                    R = __dadd_rn(R, p.mu[r]);
+                    S += (R < neg_x) ? 1 : 0;
+                }
+            }
         }
         S = __reduce_add_sync(0xffffffffu, S);
         if (lane == 0) {

@@ -113,6 +113,24 @@ void tc_build(int N, int rows, const double* A, const double* c, const double* p
 cudaError_t tc_occupancy(int rows, bool portfolio, int* blocks_per_sm);
 cudaError_t tc_launch(int N, int rows, const TcLaunch& l, int grid, cudaStream_t s);
 
+// ---- tensor-core row-slab path for N > 128 (mcr_tc.cu) --------------------------------------------
+struct SlabLaunch {
+    uint64_t M, path_offset;
+    uint32_t key0, key1;
+    int32_t ncols;               // normal columns this slab multiplies
+    double delta_rel, delta_abs; // unscaled guard band of this slab
+    const void* d_slab_image;    // device image of this slab (slab_build)
+    uint16_t* S_acc;             // [M] running per-trial hit count, bit 15 = flagged
+    int32_t first_slab;
+};
+int slab_count(int N);
+int slab_ncols(int N, int t, bool lower);
+size_t slab_image_bytes(int N, bool lower);
+void slab_build(int N, bool lower, const double* A, const double* c, uint8_t* image, size_t* offsets);
+cudaError_t slab_launch(const SlabLaunch& l, int num_sms, cudaStream_t s);
+cudaError_t slab_count_launch(uint64_t M, const uint16_t* S_acc, int k, int32_t* S_out, uint32_t* flag_list,
+                              uint32_t* flag_count, uint32_t flag_cap, uint64_t* block_partials, int grid, cudaStream_t s);
+
 cudaError_t launch_dump(uint64_t M, uint64_t path_offset, uint32_t key0, uint32_t key1, int N,
                         float* dZ, uint32_t* dU, cudaStream_t s);
 cudaError_t launch_fp32_peak(int grid, int iters, float* sink, cudaStream_t s);

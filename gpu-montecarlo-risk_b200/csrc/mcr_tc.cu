@@ -453,6 +453,239 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
     if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+// ======================================================================================================
+// Large asset counts (N > 128): row slabs.
+//
+// 128 trials x N accumulators do not fit TMEM (512 columns) and the transform does not fit shared memory,
+// so the correlate is done one slab of 128 transform rows at a time: slab t needs the normals of
+// columns [0, ncols_t) only (ncols_t = min(N, 128 (t+1)) for a lower-triangular transform), which the
+// generator simply re-derives from the counter-based stream, and its 128 x 64 transform K-blocks are
+// streamed from L2 into the same ring slot as the Z K-block they multiply.  Each launch adds the slab's
+// hit count into a per-trial uint16 (bit 15 = "inside the guard band in some slab"); slab_count_kernel
+// then reduces that array exactly like the single-launch kernels do.  Costs: the normals are generated
+// about (slabs + 1) / 2 times, and 4 bytes of HBM traffic per trial and slab.
+// ======================================================================================================
+struct TcSlabParams {
+    uint64_t M, path_offset;
+    uint32_t key0, key1;
+    int32_t ncols;        // normal columns this slab multiplies; the constant 1 sits in column ncols
+    int32_t kb_count;     // K-blocks = ceil((ncols + 1) / 64)
+    float delta_rel, delta_abs;   // scaled guard band = delta_rel * ||z||_2 + delta_abs (Cauchy-Schwarz bound on sum |a||z|)
+    const uint4* B_slab;  // global: kb_count x [hi 16 KB | lo 16 KB], rows x 128 B, pre-swizzled
+    uint16_t* S_acc;      // [M] running hit count, bit 15 = flagged
+    int32_t first_slab;   // overwrite S_acc instead of accumulating
+};
+
+constexpr int SLAB_ROWS = 128;
+constexpr uint32_t SLAB_Z_BYTES = 2 * tc::TILE_M * 128;    // Z K-block: hi + lo
+constexpr uint32_t SLAB_B_BYTES = 2 * SLAB_ROWS * 128;     // B K-block: hi + lo
+constexpr uint32_t SLAB_SLOT_BYTES = SLAB_Z_BYTES + SLAB_B_BYTES;
+constexpr int SLAB_KSPLIT = 4;                             // generator threads per trial row (each owns 16 of a K-block's 64 columns)
+constexpr int SLAB_GEN_THREADS = 128 * SLAB_KSPLIT;
+constexpr int SLAB_THREADS = SLAB_GEN_THREADS + 32;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory"); }
+
+// 16 generator warps: warp w works on trial rows 32 (w % 4) .. +31 (its TMEM lane quadrant) and on columns
+// 16 (w / 4) .. +15 of every K-block while generating, accumulator columns 32 (w / 4) .. +31 in the epilogue.
+__global__ void __launch_bounds__(SLAB_THREADS, 1) tc_slab_kernel(const TcSlabParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t s_empty[2], s_done[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_part_S[2][SLAB_KSPLIT][128];
+    __shared__ float s_part_band[2][SLAB_KSPLIT][128], s_part_zmax[2][SLAB_KSPLIT][128];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr uint32_t TMEM_COLS = 256;   // two accumulator regions of 128 columns
+    constexpr int MMA_WARP = SLAB_GEN_THREADS / 32;
+
+    if (tid == 0)
+        for (int b = 0; b < 2; ++b) { mbar_init(&s_empty[b], 1); mbar_init(&s_done[b], 1); }
+    if (warp == MMA_WARP) tmem_alloc(&s_tmem, TMEM_COLS);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+
+    const uint64_t n_tiles = (p.M + TILE_M - 1) / TILE_M;
+    const uint64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    constexpr uint32_t IDESC = make_idesc(SLAB_ROWS);
+    const int KBN = p.kb_count;
+
+    if (warp == MMA_WARP) {
+        for (uint64_t n = 0; n < my_tiles; ++n) {
+            for (int kb = 0; kb < KBN; ++kb) {
+                const uint32_t u = (uint32_t)(n * KBN + kb), slot = u & 1;
+                named_bar_sync(1 + slot, SLAB_THREADS);
+                if (lane == 0) {
+                    tc_fence_after();
+                    const uint32_t zhi = smem_u32(smem + slot * SLAB_SLOT_BYTES), zlo = zhi + TILE_M * 128;
+                    const uint32_t bhi = zhi + SLAB_Z_BYTES, blo = bhi + SLAB_ROWS * 128;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(n & 1) * 128;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t za = pass == 2 ? zlo : zhi;
+                        const uint32_t ba = pass == 1 ? blo : bhi;
+#pragma unroll
+                        for (int ks = 0; ks < KBLOCK / 16; ++ks)
+                            umma_f16(d_tmem, make_desc(za + ks * 32), make_desc(ba + ks * 32), IDESC, (kb | pass | ks) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&s_empty[slot]);
+                    if (kb == KBN - 1) umma_commit(&s_done[n & 1]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int row = tid & 127, part = tid >> 7;   // part: K-split index while generating, column quarter in the epilogue
+        const uint32_t ring_row = smem_u32(smem) + (uint32_t)(row / 8) * 1024u + (uint32_t)(row % 8) * 128u;
+        const uint32_t r7s = (uint32_t)(row % 8) << 4;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)part * 32;
+        const int n_full = p.ncols / 8;
+        uint32_t empty_phase = 0, done_phase = 0;
+        float prev_zmax = 0.0f;
+        uint64_t prev_i = 0;
+
+        auto epilogue = [&](uint64_t n, uint64_t i, float zmax) {
+            const uint32_t r = (uint32_t)(n & 1);
+            mbar_wait(&s_done[r], (done_phase >> r) & 1u);
+            done_phase ^= 1u << r;
+            tc_fence_after();
+            uint32_t S = 0;
+            float band = 3.0e38f;
+            {
+                uint32_t v[32];
+                tmem_ld32(taddr + r * 128, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    S += v[c] >> 31;
+                    band = fminf(band, fabsf(__uint_as_float(v[c])));
+                }
+            }
+            tc_fence_before();
+            s_part_S[r][part][row] = S;
+            s_part_band[r][part][row] = band;
+            s_part_zmax[r][part][row] = zmax;
+            named_bar_sync(3, SLAB_GEN_THREADS);   // the four column quarters of every row are in
+            if (part == 0 && i < p.M) {
+#pragma unroll
+                for (int q = 1; q < SLAB_KSPLIT; ++q) {
+                    S += s_part_S[r][q][row];
+                    band = fminf(band, s_part_band[r][q][row]);
+                    zmax += s_part_zmax[r][q][row];   // total sum of squares of the trial's normals in this slab
+                }
+                const uint32_t flagged = band < __fmaf_rn(p.delta_rel, sqrtf(zmax) * 1.0001f, p.delta_abs) ? 0x8000u : 0u;
+                const uint32_t old = p.first_slab ? 0u : (uint32_t)p.S_acc[i];
+                p.S_acc[i] = (uint16_t)(((old & 0x7FFFu) + S) | (old & 0x8000u) | flagged);
+            }
+        };
+
+        for (uint64_t n = 0; n < my_tiles; ++n) {
+            const uint64_t tile = blockIdx.x + (uint64_t)gridDim.x * n;
+            const uint64_t i = tile * TILE_M + row;
+            const uint64_t path = p.path_offset + i;
+            PhiloxPath rng;
+            rng.init((uint32_t)path, (uint32_t)(path >> 32), p.key1);
+            float zmax = 0.0f;
+#pragma unroll 1
+            for (int kb = 0; kb < KBN; ++kb) {
+                const uint32_t u = (uint32_t)(n * KBN + kb), slot = u & 1;
+                if (u >= 2) {
+                    mbar_wait(&s_empty[slot], (empty_phase >> slot) & 1u);
+                    empty_phase ^= 1u << slot;
+                }
+                // the slab's transform K-block: 32 KB from the pre-swizzled global image (L2 resident), asynchronous
+                {
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.B_slab) + (size_t)kb * SLAB_B_BYTES;
+                    const uint32_t dst = smem_u32(smem + slot * SLAB_SLOT_BYTES + SLAB_Z_BYTES);
+#pragma unroll
+                    for (int q = 0; q < (int)(SLAB_B_BYTES / 16 / SLAB_GEN_THREADS); ++q)
+                        cp_async16(dst + 16 * (tid + SLAB_GEN_THREADS * q), src + 16 * (tid + SLAB_GEN_THREADS * q));
+                }
+                const uint32_t zhi_row = ring_row + slot * SLAB_SLOT_BYTES, zlo_row = zhi_row + TILE_M * 128;
+                // this thread's two chunks (16 columns) of the K-block
+                const int c0 = 8 * kb + 2 * part;
+                if (c0 + 2 <= n_full) {
+                    float z[16];
+                    rng.normals_multi<4>((uint32_t)(2 * c0), p.key0, p.key1, z);
+                    float unused = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) zmax = fmaf(z[q], z[q], zmax);   // here "zmax" carries sum z^2
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        float zc[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) zc[q] = z[8 * w + q];
+                        store_chunk(zc, 2 * part + w, zhi_row, zlo_row, r7s, unused);
+                    }
+                } else {
+                    for (int c8 = c0; c8 < c0 + 2; ++c8) {   // chunks touching the end of the normal columns
+                        float z[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) z[q] = 0.0f;
+                        if (8 * c8 < p.ncols) rng.normals((uint32_t)(2 * c8), p.key0, p.key1, z);
+                        if (8 * c8 + 4 < p.ncols) rng.normals((uint32_t)(2 * c8 + 1), p.key0, p.key1, z + 4);
+                        float zmax_unused = 0.0f;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (8 * c8 + q < p.ncols) zmax = fmaf(z[q], z[q], zmax);
+                            if (8 * c8 + q == p.ncols) z[q] = 1.0f;
+                            if (8 * c8 + q > p.ncols) z[q] = 0.0f;
+                        }
+                        store_chunk(z, c8 - 8 * kb, zhi_row, zlo_row, r7s, zmax_unused);
+                    }
+                }
+                cp_async_wait_all();
+                fence_async_smem();
+                if (kb == 0) tc_fence_before();
+                named_bar_arrive(1 + slot, SLAB_THREADS);
+            }
+            if (n > 0) epilogue(n - 1, prev_i, prev_zmax);
+            prev_i = i;
+            prev_zmax = zmax;
+        }
+        if (my_tiles > 0) epilogue(my_tiles - 1, prev_i, prev_zmax);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// reduce the per-trial slab sums: flagged trials go to the fp64 fix-up list, the rest are counted
+__global__ void __launch_bounds__(256) slab_count_kernel(uint64_t M, const uint16_t* S_acc, int k, int32_t* S_out,
+                                                         uint32_t* flag_list, uint32_t* flag_count, uint32_t flag_cap,
+                                                         uint64_t* block_partials) {
+    uint32_t cnt = 0, sum_s = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = S_acc[i];
+        if (v & 0x8000u) {
+            const uint32_t slot = atomicAdd(flag_count, 1u);
+            if (slot < flag_cap) flag_list[slot] = (uint32_t)i;
+        } else {
+            cnt += (v >= (uint32_t)k) ? 1u : 0u;
+            sum_s += v;
+            if (S_out) S_out[i] = (int32_t)v;
+        }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    sum_s = __reduce_add_sync(0xffffffffu, sum_s);
+    __shared__ uint32_t s_c[8], s_s[8];
+    if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5] = cnt; s_s[threadIdx.x >> 5] = sum_s; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t c = 0, s = 0;
+        for (int w = 0; w < 8; ++w) { c += s_c[w]; s += s_s[w]; }
+        block_partials[2 * (uint64_t)blockIdx.x] = c;
+        block_partials[2 * (uint64_t)blockIdx.x + 1] = s;
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 // Transform image: rows i < N hold A_ij * 2^10 (columns j < N) and (mu_i + x) * 2^10 (column N); padded
 // rows hold +2^10 in column N so they are always far on the "no crash" side.  Everything is split into
@@ -578,6 +811,68 @@ cudaError_t tc_launch(int N, int rows, const TcLaunch& l, int grid, cudaStream_t
     p.hist_lo = (float)l.hist_lo; p.hist_inv_w = (float)(1.0 / l.hist_width);
     p.port_acc = l.port_acc; p.port_hist = l.port_hist; p.port_hist_sum = l.port_hist_sum;
     return tc_find(rows)->launch(p, grid, s);
+}
+
+// ---- slab path host side ---------------------------------------------------------------------------------
+int slab_count(int N) { return (N + SLAB_ROWS - 1) / SLAB_ROWS; }
+int slab_ncols(int N, int t, bool lower) { return lower ? std::min(N, SLAB_ROWS * (t + 1)) : N; }
+int slab_kblocks(int ncols) { return (ncols + 1 + tc::KBLOCK - 1) / tc::KBLOCK; }
+
+size_t slab_image_bytes(int N, bool lower) {
+    size_t b = 0;
+    for (int t = 0; t < slab_count(N); ++t) b += (size_t)slab_kblocks(slab_ncols(N, t, lower)) * SLAB_B_BYTES;
+    return b;
+}
+
+// image of every slab, back to back; offsets[t] = byte offset of slab t (offsets has slab_count(N) + 1 entries)
+void slab_build(int N, bool lower, const double* A, const double* c, uint8_t* image, size_t* offsets) {
+    size_t off = 0;
+    for (int t = 0; t < slab_count(N); ++t) {
+        offsets[t] = off;
+        const int ncols = slab_ncols(N, t, lower), kbn = slab_kblocks(ncols);
+        uint8_t* img = image + off;
+        memset(img, 0, (size_t)kbn * SLAB_B_BYTES);
+        for (int r = 0; r < SLAB_ROWS; ++r) {
+            const int i = SLAB_ROWS * t + r;
+            for (int k = 0; k <= ncols; ++k) {
+                double v;
+                if (k < ncols) v = (i < N) ? A[(size_t)i * N + k] : 0.0;
+                else v = (i < N) ? c[i] : 1.0;
+                v *= TC_SCALE;
+                const __half hi = __float2half_rn((float)v);
+                const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+                // K-block kb = k / 64: [hi: 128 rows x 128 B][lo: ...], same swizzle as the device-side Z rows
+                const int kb = k / tc::KBLOCK, kk = k % tc::KBLOCK;
+                const size_t o = (size_t)kb * SLAB_B_BYTES + (size_t)(r / 8) * 1024 + (size_t)(r % 8) * 128 +
+                                 (size_t)(((kk / 8) ^ (r % 8)) * 16) + (size_t)(kk % 8) * 2;
+                memcpy(img + o, &hi, 2);
+                memcpy(img + o + SLAB_ROWS * 128, &lo, 2);
+            }
+        }
+        off += (size_t)kbn * SLAB_B_BYTES;
+    }
+    offsets[slab_count(N)] = off;
+}
+
+cudaError_t slab_launch(const SlabLaunch& l, int num_sms, cudaStream_t s) {
+    const size_t smem = 2 * (size_t)SLAB_SLOT_BYTES + 1024;
+    cudaError_t e = cudaFuncSetAttribute(tc_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    TcSlabParams p{};
+    p.M = l.M; p.path_offset = l.path_offset; p.key0 = l.key0; p.key1 = l.key1;
+    p.ncols = l.ncols; p.kb_count = slab_kblocks(l.ncols);
+    p.delta_rel = (float)(l.delta_rel * TC_SCALE); p.delta_abs = (float)(l.delta_abs * TC_SCALE);
+    p.B_slab = reinterpret_cast<const uint4*>(l.d_slab_image); p.S_acc = l.S_acc; p.first_slab = l.first_slab;
+    const uint64_t tiles = (l.M + tc::TILE_M - 1) / tc::TILE_M;
+    const int grid = (int)std::min<uint64_t>((uint64_t)num_sms, tiles ? tiles : 1);
+    tc_slab_kernel<<<grid, SLAB_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t slab_count_launch(uint64_t M, const uint16_t* S_acc, int k, int32_t* S_out, uint32_t* flag_list,
+                              uint32_t* flag_count, uint32_t flag_cap, uint64_t* block_partials, int grid, cudaStream_t s) {
+    slab_count_kernel<<<grid, 256, 0, s>>>(M, S_acc, k, S_out, flag_list, flag_count, flag_cap, block_partials);
+    return cudaGetLastError();
 }
 
 }  // namespace mcr

@@ -281,17 +281,25 @@ def test_kernel_selection(engine):
         engine.run_with_normals(Z, m.x, m.k, kernel=api.KERNEL_TENSOR)
 
 
-def test_large_n_falls_back_to_gpu_exact_kernel(engine, oracle):
-    m = synthetic_model(160)
-    A = engine.upload_sigma(m.mu, m.Sigma)
-    Z, _ = engine.dump_normals(5000, 11)
+@pytest.mark.parametrize("N,mode,M", [(160, api.TRANSFORM_LOWER, 20000), (200, api.TRANSFORM_GSL_FULL, 8000),
+                                      (600, api.TRANSFORM_LOWER, 5000)])
+def test_large_n_row_slab_tensor_kernel_bit_exact(engine, oracle, N, mode, M):
+    """N > 128 (Stoxx600 shape): tensor-core kernel over row slabs of 128 assets; still bit-exact."""
+    m = synthetic_model(N)
+    A = engine.upload_sigma(m.mu, m.Sigma, mode)
+    Z, _ = engine.dump_normals(M, 11, path_offset=77)
     ro = oracle.run_normals(A, m.mu, m.k, m.x, Z)
-    r = engine.run(5000, 11, m.x, m.k)
-    assert r.kernel == "exact" and (r.count, r.sum_S) == (ro["count"], ro["sum_S"])
+    r = engine.run(M, 11, m.x, m.k, path_offset=77)
+    assert r.kernel == "tensor" and r.padded_N >= N
+    assert (r.count, r.sum_S, r.n_paths) == (ro["count"], ro["sum_S"], M)
+    rx = engine.run(M, 11, m.x, m.k, path_offset=77, kernel=api.KERNEL_EXACT)
+    assert rx.kernel == "exact" and (rx.count, rx.sum_S) == (ro["count"], ro["sum_S"])
+    Z0, _ = engine.dump_normals(M, 11)
+    r0 = oracle.run_normals(A, m.mu, m.k, m.x, Z0)
+    h = api.simulate_host(m.mu, A, M, 11, m.x, m.k, a_is_lower=(mode == api.TRANSFORM_LOWER), want_S_values=True)
+    np.testing.assert_array_equal(h.S_values, r0["S_values"])
     with pytest.raises(api.McrError, match="no FFMA instantiation"):
-        engine.run(5000, 11, m.x, m.k, kernel=api.KERNEL_FFMA)
-    with pytest.raises(api.McrError, match="tensor-core kernel covers"):
-        engine.run(5000, 11, m.x, m.k, kernel=api.KERNEL_TENSOR)
+        engine.run(1000, 11, m.x, m.k, kernel=api.KERNEL_FFMA)
 
 
 def test_error_behaviour():

@@ -18,7 +18,8 @@ if __name__ == "__main__":
     if sys.argv[1] == "--child":
         child(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]); sys.exit(0)
     M = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
-    for N in (50, 100, 128, 25):
+    Ns = [int(a) for a in sys.argv[2:]] or [50, 100, 128, 25]
+    for N in Ns:
         def run(kernel, scale=None):
             env = dict(os.environ)
             if scale is not None: env["MCR_TC_BAND_SCALE"] = str(scale)
