@@ -294,7 +294,14 @@ def main():
                 h = api.simulate_host(mu_h, A_h, M, SEED, model.x, model.k, a_is_lower=True, reupload=True)
             dt = (time.perf_counter() - t0) / nrep
             assert (h.count, h.sum_S) == (one.count, one.sum_S)
-            e2e = {"value": M / dt, "unit": "simulations/s",
+            # same call when the caller asks for the reference's per-trial S_values array (4*M bytes D2H)
+            t0 = time.perf_counter()
+            hs = api.simulate_host(mu_h, A_h, M, SEED, model.x, model.k, a_is_lower=True, reupload=True, want_S_values=True)
+            dt_s = time.perf_counter() - t0
+            assert int(hs.S_values.sum()) == one.sum_S
+            e2e_s = {"value": M / dt_s, "ms_per_step": dt_s * 1e3, "d2h_bytes_per_step": 4 * M + 64,
+                     "note": "with MonteCarloResult.S_values filled (the reference always does; nothing reads it)"}
+            e2e = {"value": M / dt, "unit": "simulations/s", "with_S_values": e2e_s,
                    "h2d_bytes_per_step": int(mu_h.nbytes + A_h.nbytes + 8 * N * N // 2),
                    "d2h_bytes_per_step": 8 * api.MCR_PARTIAL_WORDS, "ms_per_step": dt * 1e3,
                    "api": "mcr_simulate_host (host mu/A in, result out; S_values not requested, as the plugin's default)"}
