@@ -282,7 +282,7 @@ def test_kernel_selection(engine):
 
 
 @pytest.mark.parametrize("N,mode,M", [(160, api.TRANSFORM_LOWER, 20000), (200, api.TRANSFORM_GSL_FULL, 8000),
-                                      (600, api.TRANSFORM_LOWER, 5000)])
+                                      (600, api.TRANSFORM_LOWER, 5000), (1024, api.TRANSFORM_LOWER, 1500)])
 def test_large_n_row_slab_tensor_kernel_bit_exact(engine, oracle, N, mode, M):
     """N > 128 (Stoxx600 shape): tensor-core kernel over row slabs of 128 assets; still bit-exact."""
     m = synthetic_model(N)

@@ -75,3 +75,17 @@ def test_reference_main_runner_drop_in(tmp_path):
     se = np.sqrt(pc * (1 - pc) / M + ps * (1 - ps) / M)
     assert abs(pc - ps) <= 3 * se + 1e-6, (pc, ps, se)   # independent RNG streams, same transform matrix
     assert "CUDA Simulation complete" in p.stdout
+
+
+def test_cli_runs_from_preprocessing_binaries(engine):
+    """mcr_cli: hardened loader (model_loader.c) -> mcr_build_transform -> mcr_simulate_host, no GSL involved."""
+    exe = PKG / "bin" / "mcr_cli"
+    assert exe.exists(), "bin/mcr_cli must be prebuilt and shipped to the GPU box"
+    p = subprocess.run([str(exe), str(GOLD / "data15"), "500000", "0.02", "5", "67", "1", "gsl_full"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    g = np.load(GOLD / "pyref_n15.npz")
+    engine.upload_sigma(g["mu"], g["Sigma"], api.TRANSFORM_GSL_FULL)
+    r = engine.run(500000, 67, 0.02, 5)
+    assert f"count={r.count} sum_S={r.sum_S} " in p.stdout
+    bad = subprocess.run([str(exe), str(GOLD)], capture_output=True, text=True, timeout=60)
+    assert bad.returncode == 1 and "Cannot open" in bad.stderr
