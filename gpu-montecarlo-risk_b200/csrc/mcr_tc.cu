@@ -141,6 +141,8 @@ struct TcParams {
     double* port_acc;             // [4] += hits, sum P, sum P^2, sum of -P over tail events
     unsigned long long* port_hist;  // [MCR_PORTFOLIO_BINS] counts
     double* port_hist_sum;          // [MCR_PORTFOLIO_BINS] per-bin sum of P
+    // the 8-column chunk holding column N: z <- z * tail_mul + tail_add  (normals | the constant 1 | zeros)
+    float tail_mul[8], tail_add[8];
 };
 
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -156,6 +158,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile
 #define MCR_TC_UNROLL 2
 #endif
 constexpr int TC_UNROLL = MCR_TC_UNROLL;  // 8-normal chunks in flight per generator thread
+
+// z - float(h) with h an fp16 value: fma.rn.f32.f16 (h * -1.0h + z), one FHFMA instruction
+__device__ __forceinline__ float sub_half(float z, unsigned short h) {
+    float d;
+    const unsigned short minus_one = 0xBC00;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(h), "h"(minus_one), "f"(z));
+    return d;
+}
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -177,9 +187,10 @@ __device__ __forceinline__ void store_chunk(const float (&z)[8], int c8, uint32_
     for (int q = 0; q < 4; ++q) {
         zmax = fmaxf(zmax, fmaxf(fabsf(z[2 * q]), fabsf(z[2 * q + 1])));
         const __half2 h = __floats2half2_rn(z[2 * q], z[2 * q + 1]);
-        const float2 f = __half22float2(h);
-        const __half2 l = __floats2half2_rn(z[2 * q] - f.x, z[2 * q + 1] - f.y);
         hv[q] = *reinterpret_cast<const uint32_t*>(&h);
+        // lo = z - float(hi) in one mixed-precision FMA each (FHFMA: f16 * f16 + f32, exact here)
+        const __half2 l = __floats2half2_rn(sub_half(z[2 * q], (unsigned short)(hv[q] & 0xffffu)),
+                                            sub_half(z[2 * q + 1], (unsigned short)(hv[q] >> 16)));
         lv[q] = *reinterpret_cast<const uint32_t*>(&l);
     }
     const uint32_t off = (((uint32_t)c8 & 7u) << 4) ^ r7s;   // c8: chunk index inside the K-block
@@ -390,18 +401,20 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
                     rng.normals_multi<2>((uint32_t)(2 * c8), p.key0, p.key1, z);
                     store_chunk(z, c8 - c_begin, zhi_row, zlo_row, r7s, zmax);
                 }
-                for (; c8 < c_begin + 8; ++c8) {   // tail chunks of the K dimension (at most 8 per tile)
+                for (; c8 < c_begin + 8; ++c8) {   // at most 8 such chunks per tile: the one holding column N, then zeros
                     float z[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) z[q] = 0.0f;
-                    if (8 * c8 < p.N) rng.normals((uint32_t)(2 * c8), p.key0, p.key1, z);
-                    if (8 * c8 + 4 < p.N) rng.normals((uint32_t)(2 * c8 + 1), p.key0, p.key1, z + 4);
-                    float zmax_unused = 0.0f;   // the constant column must not enter max|z|
+                    float zmax_unused = 0.0f;
+                    if (c8 == n_full) {
+                        if (p.N - 8 * c8 > 4) rng.normals_multi<2>((uint32_t)(2 * c8), p.key0, p.key1, z);
+                        else if (p.N - 8 * c8 > 0) rng.normals((uint32_t)(2 * c8), p.key0, p.key1, z);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (8 * c8 + q < p.N) zmax = fmaxf(zmax, fabsf(z[q]));
-                        if (8 * c8 + q == p.N) z[q] = 1.0f;
-                        if (8 * c8 + q > p.N) z[q] = 0.0f;
+                        for (int q = 0; q < 8; ++q) {
+                            const float zq = z[q] * p.tail_mul[q];        // normals of columns < N, zeros otherwise
+                            zmax = fmaxf(zmax, fabsf(zq));
+                            z[q] = zq + p.tail_add[q];                    // the constant 1 in column N
+                        }
                     }
                     store_chunk(z, c8 - c_begin, zhi_row, zlo_row, r7s, zmax_unused);
                 }
@@ -810,6 +823,11 @@ cudaError_t tc_launch(int N, int rows, const TcLaunch& l, int grid, cudaStream_t
     p.portfolio = l.portfolio; p.port_thresh = (float)(-l.port_x * TC_SCALE);
     p.hist_lo = (float)l.hist_lo; p.hist_inv_w = (float)(1.0 / l.hist_width);
     p.port_acc = l.port_acc; p.port_hist = l.port_hist; p.port_hist_sum = l.port_hist_sum;
+    for (int q = 0; q < 8; ++q) {
+        const int col = 8 * (N / 8) + q;
+        p.tail_mul[q] = col < N ? 1.0f : 0.0f;
+        p.tail_add[q] = col == N ? 1.0f : 0.0f;
+    }
     return tc_find(rows)->launch(p, grid, s);
 }
 

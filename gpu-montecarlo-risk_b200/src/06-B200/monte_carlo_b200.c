@@ -13,6 +13,8 @@
  *     MCR_S_VALUES=1, which saves a 4*M-byte device buffer and D2H copy;
  *   - the transform convention is selectable (MCR_TRANSFORM=lower|gsl_full, see cholesky_upload.h);
  *   - paths can be sharded over MCR_NUM_GPUS devices with one NCCL all-reduce;
+ *   - MCR_TIMING_CSV=<path> appends the device-timed ms / sims/s of every run to a sibling CSV (the driver's
+ *     own results row keeps its wall-clock execution_time_ms, csv_writer.c:41-45);
  *   - all CUDA work happens in libmcr_b200.so through its C ABI (include/mcr_b200.h); this file is
  *     plain C and has no CPU compute fallback.
  * No config struct reaches a model (model_interface.h:30), hence the environment variables.
@@ -97,6 +99,24 @@ static int b200_simulate(MonteCarloParams *params, MonteCarloResult *result) {
     result->std_error = r.std_error;
     result->ci_lower = r.ci_lower;
     result->ci_upper = r.ci_upper;
+    /* F2: device-side timing next to the driver's wall-clock row, without touching its 22-column schema:
+     * MCR_TIMING_CSV=<path> appends one line per run (header written once). */
+    {
+        const char *tpath = getenv("MCR_TIMING_CSV");
+        if (tpath && *tpath) {
+            FILE *probe = fopen(tpath, "r");
+            FILE *f = fopen(tpath, "a");
+            if (f) {
+                if (!probe) fprintf(f, "model_name,N,M,k,x,seed,n_gpus,kernel,padded_N,launches,device_ms,sims_per_s,rechecked,count,P_hat\n");
+                fprintf(f, "cuda,%d,%d,%d,%.6f,%lu,%d,%d,%d,%d,%.4f,%.6e,%llu,%llu,%.9f\n", params->N, params->M, params->k, params->x,
+                        params->random_seed, req.n_gpus > 0 ? req.n_gpus : 1, r.kernel_used, r.padded_N, r.launches, r.device_ms,
+                        r.device_ms > 0 ? (double)r.n_paths / (r.device_ms * 1e-3) : 0.0, (unsigned long long)r.n_rechecked,
+                        (unsigned long long)r.count, r.P_hat);
+                fclose(f);
+            }
+            if (probe) fclose(probe);
+        }
+    }
     printf("CUDA Simulation complete (kernel=%d, padded N=%d, %d launches, device time %.3f ms, %.3e simulations/s, "
            "%llu trials rechecked in fp64)\n",
            r.kernel_used, r.padded_N, r.launches, r.device_ms,

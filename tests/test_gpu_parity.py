@@ -281,6 +281,20 @@ def test_kernel_selection(engine):
         engine.run_with_normals(Z, m.x, m.k, kernel=api.KERNEL_TENSOR)
 
 
+@pytest.mark.parametrize("N", [50, 100, 160])
+def test_tensor_kernels_ragged_trial_counts_and_offsets(engine, oracle, N):
+    """Tiles are 128 trials: partial tiles, fewer tiles than CTAs, tile counts not divisible by the number of
+    generator groups, and a path range crossing 2^32 (Philox counter carry)."""
+    m = synthetic_model(N)
+    A = engine.upload_sigma(m.mu, m.Sigma)
+    for M, off in ((1, 0), (127, 5), (128, 0), (129, 7), (385, (1 << 32) - 100), (148 * 128 * 3 + 17, 12345)):
+        Z, _ = engine.dump_normals(M, 9, path_offset=off)
+        ro = oracle.run_normals(A, m.mu, m.k, m.x, Z)
+        r = engine.run(M, 9, m.x, m.k, path_offset=off, kernel=api.KERNEL_TENSOR)
+        assert r.kernel == "tensor" and (r.count, r.sum_S, r.n_paths) == (ro["count"], ro["sum_S"], M), (N, M, off)
+    assert engine.run(0, 9, m.x, m.k, kernel=api.KERNEL_TENSOR).n_paths == 0
+
+
 @pytest.mark.parametrize("N,mode,M", [(160, api.TRANSFORM_LOWER, 20000), (200, api.TRANSFORM_GSL_FULL, 8000),
                                       (600, api.TRANSFORM_LOWER, 5000), (1024, api.TRANSFORM_LOWER, 1500)])
 def test_large_n_row_slab_tensor_kernel_bit_exact(engine, oracle, N, mode, M):

@@ -64,7 +64,7 @@ def test_reference_main_runner_drop_in(tmp_path):
     for f in ("mu.bin", "sigma.bin", "params.bin"):
         shutil.copy(GOLD / "data15" / f, tmp_path / "data" / f)
     shutil.copy(GOLD / "config_dropin.yaml", tmp_path / "config.yaml")
-    env = dict(os.environ, MCR_TRANSFORM="gsl_full", OMP_NUM_THREADS="2")
+    env = dict(os.environ, MCR_TRANSFORM="gsl_full", OMP_NUM_THREADS="2", MCR_TIMING_CSV=str(tmp_path / "results" / "b200_timing.csv"))
     p = subprocess.run([str(exe)], cwd=tmp_path, stdin=subprocess.DEVNULL, capture_output=True, text=True, env=env, timeout=300)
     assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
     rows = list(csv.DictReader(open(tmp_path / "results" / "simulation_results.csv")))
@@ -75,6 +75,9 @@ def test_reference_main_runner_drop_in(tmp_path):
     se = np.sqrt(pc * (1 - pc) / M + ps * (1 - ps) / M)
     assert abs(pc - ps) <= 3 * se + 1e-6, (pc, ps, se)   # independent RNG streams, same transform matrix
     assert "CUDA Simulation complete" in p.stdout
+    timing = list(csv.DictReader(open(tmp_path / "results" / "b200_timing.csv")))
+    assert len(timing) == 1 and int(timing[0]["M"]) == M and float(timing[0]["device_ms"]) > 0
+    assert int(timing[0]["count"]) == int(rows[0]["count"])
 
 
 def test_cli_runs_from_preprocessing_binaries(engine):
