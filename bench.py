@@ -44,7 +44,7 @@ def flops_per_sim(N):
 class ClockSampler:
     """Samples SM clock and throttle reasons during the timed region (NVML; nvidia-smi fallback)."""
 
-    def __init__(self, index=0, period=0.1):
+    def __init__(self, index=0, period=0.02):
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()

@@ -155,6 +155,7 @@ int mcr_create(int device, mcr_engine** out) {
     ok(cudaMalloc(&e->d_accum, sizeof(unsigned long long) * 2));
     ok(cudaMalloc(&e->d_block_partials, sizeof(uint64_t) * 2 * MAX_GRID));
     ok(cudaMalloc(&e->d_partials, sizeof(uint64_t) * MCR_PARTIAL_WORDS));
+    ok(cudaMalloc(&e->d_hist, sizeof(unsigned long long) * MCR_MAX_HIST));
     ok(cudaMalloc(&e->d_port_acc, sizeof(double) * 4));
     ok(cudaMalloc(&e->d_port_hist, sizeof(unsigned long long) * MCR_PORTFOLIO_BINS));
     ok(cudaMalloc(&e->d_port_hist_sum, sizeof(double) * MCR_PORTFOLIO_BINS));
@@ -175,6 +176,7 @@ int mcr_destroy(mcr_engine* e) {
     cudaFree(e->d_flag_list); cudaFree(e->d_flag_count); cudaFree(e->d_accum);
     cudaFree(e->d_block_partials); cudaFree(e->d_partials);
     cudaFree(e->d_port_acc); cudaFree(e->d_port_hist); cudaFree(e->d_port_hist_sum);
+    cudaFree(e->d_hist); cudaFree(e->d_S_tmp);
     if (e->h_partials) cudaFreeHost(e->h_partials);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -323,6 +325,23 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     int32_t* d_S = opt ? opt->d_S_values : nullptr;
     int launches = 0;
+    // histogram of S: needs the per-trial S of every chunk; use the caller's buffer or a per-chunk scratch one
+    const bool want_hist = opt && opt->want_hist;
+    bool S_is_scratch = false;
+    if (want_hist) {
+        MCR_CUDA(cudaMemsetAsync(e->d_hist, 0, sizeof(unsigned long long) * MCR_MAX_HIST, s));
+        if (!d_S) {
+            const uint64_t need = std::min<uint64_t>(M, CHUNK_PATHS);
+            if (e->S_tmp_cap < need) {
+                cudaFree(e->d_S_tmp); e->d_S_tmp = nullptr; e->S_tmp_cap = 0;
+                MCR_CUDA(cudaMalloc(&e->d_S_tmp, sizeof(int32_t) * std::max<uint64_t>(need, 1)));
+                e->S_tmp_cap = need;
+            }
+            d_S = e->d_S_tmp;
+            S_is_scratch = true;
+        }
+    }
+    e->last_hist = want_hist;
     e->n_timed = 0;
 
     MCR_CUDA(cudaMemsetAsync(d_out, 0, sizeof(uint64_t) * MCR_PARTIAL_WORDS, s));
@@ -504,7 +523,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         xp.N = N; xp.k = k; xp.lower = e->lower ? 1 : 0; xp.x = x;
         xp.mu = e->d_mu; xp.A_cm = e->d_Acm;
         xp.Z = dZ ? dZ + done * (uint64_t)N : nullptr;
-        xp.S_out = d_S ? d_S + done : nullptr;
+        xp.S_out = d_S ? (S_is_scratch ? d_S : d_S + done) : nullptr;
         xp.accum = e->d_accum;
         if (plan.slab) {
             const int ns = slab_count(N);
@@ -574,6 +593,10 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         }
         MCR_CUDA(launch_finalize(fin, s));
         ++launches;
+        if (want_hist) {
+            MCR_CUDA(launch_hist(m, xp.S_out, N + 1, e->d_hist, e->num_sms, s));
+            ++launches;
+        }
     }
     e->last_kernel = plan.kernel; e->last_NT = plan.NT; e->last_launches = launches; e->last_portfolio = plan.portfolio;
     return 0;
@@ -641,10 +664,11 @@ int mcr_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, doub
             const mcr_run_options* opt, mcr_result* out) {
     if (!e || !out) return fail("mcr_run: null argument");
     if (set_device(e)) return -1;
-    if (opt && opt->want_hist) return fail("mcr_run: want_hist is not built yet (use S_values)");
     MCR_CUDA(cudaEventRecord(e->ev0, e->stream));
     if (enqueue_run(e, M, path_offset, seed, x, k, opt, nullptr, e->d_partials, e->stream)) return -1;
     const int rc = finish_sync(e, out);
+    if (rc == 0 && e->last_hist)
+        MCR_CUDA(cudaMemcpy(out->hist_S, e->d_hist, sizeof(uint64_t) * MCR_MAX_HIST, cudaMemcpyDeviceToHost));
     if (rc == 0 && e->last_portfolio) {
         double acc[4];
         MCR_CUDA(cudaMemcpy(acc, e->d_port_acc, sizeof(acc), cudaMemcpyDeviceToHost));

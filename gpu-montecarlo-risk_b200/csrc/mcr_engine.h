@@ -65,6 +65,11 @@ struct mcr_engine {
     double* d_port_hist_sum = nullptr;
     double port_hist_lo = 0, port_hist_hi = 0;
     bool last_portfolio = false;
+    // histogram of S (want_hist): device bins + a per-chunk S buffer when the caller supplied none
+    unsigned long long* d_hist = nullptr;
+    int32_t* d_S_tmp = nullptr;
+    uint64_t S_tmp_cap = 0;
+    bool last_hist = false;
     // last async run bookkeeping
     int last_kernel = 0, last_NT = 0, last_launches = 0;
 };

@@ -10,6 +10,8 @@
 #include "mcr_rng.cuh"
 #include "../../include/mcr_b200.h"
 
+#include <algorithm>
+
 namespace mcr {
 
 constexpr int EXACT_WARPS = 4;
@@ -129,6 +131,29 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams p) {
 
 cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t s) {
     finalize_kernel<<<1, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ---- histogram of S over the per-trial output (extension F3: distribution of the crash count) ----------
+__global__ void __launch_bounds__(256) hist_kernel(uint64_t M, const int32_t* S, int nbins, unsigned long long* hist) {
+    extern __shared__ unsigned int s_h[];
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) s_h[b] = 0u;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int v = S[i];
+        // most trials share a few values of S: aggregate equal values inside the warp before the shared atomic
+        const unsigned peers = __match_any_sync(__activemask(), v);
+        if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&s_h[v < nbins ? v : nbins - 1], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+        if (s_h[b]) atomicAdd(&hist[b], (unsigned long long)s_h[b]);
+}
+
+cudaError_t launch_hist(uint64_t M, const int32_t* S, int nbins, unsigned long long* hist, int num_sms, cudaStream_t s) {
+    const int grid = (int)std::min<uint64_t>((uint64_t)num_sms * 8, (M + 255) / 256);
+    if (grid <= 0) return cudaSuccess;
+    hist_kernel<<<grid, 256, sizeof(unsigned int) * nbins, s>>>(M, S, nbins, hist);
     return cudaGetLastError();
 }
 

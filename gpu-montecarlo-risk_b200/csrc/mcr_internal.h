@@ -131,6 +131,7 @@ cudaError_t slab_launch(const SlabLaunch& l, int num_sms, cudaStream_t s);
 cudaError_t slab_count_launch(uint64_t M, const uint16_t* S_acc, int k, int32_t* S_out, uint32_t* flag_list,
                               uint32_t* flag_count, uint32_t flag_cap, uint64_t* block_partials, int grid, cudaStream_t s);
 
+cudaError_t launch_hist(uint64_t M, const int32_t* S, int nbins, unsigned long long* hist, int num_sms, cudaStream_t s);
 cudaError_t launch_dump(uint64_t M, uint64_t path_offset, uint32_t key0, uint32_t key1, int N,
                         float* dZ, uint32_t* dU, cudaStream_t s);
 cudaError_t launch_fp32_peak(int grid, int iters, float* sink, cudaStream_t s);

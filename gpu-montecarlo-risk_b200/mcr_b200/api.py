@@ -45,6 +45,7 @@ class RunResult:
     launches: int
     S_values: np.ndarray = None
     portfolio: dict = None   # extension outputs of a want_portfolio run (see Engine.run)
+    hist_S: np.ndarray = None  # hist_S[s] = #{trials with S == s} (want_hist)
 
     @staticmethod
     def from_c(r: Result, S_values=None):
@@ -53,12 +54,13 @@ class RunResult:
                          int(r.padded_N), int(r.launches), S_values)
 
 
-def make_options(kernel=KERNEL_AUTO, no_recheck=False, d_S_values=0, portfolio_threshold=None) -> RunOptions:
+def make_options(kernel=KERNEL_AUTO, no_recheck=False, d_S_values=0, portfolio_threshold=None, want_hist=False) -> RunOptions:
     o = RunOptions()
     o.struct_size = C.sizeof(RunOptions)
     o.kernel = int(kernel)
     o.no_recheck = int(bool(no_recheck))
     o.d_S_values = d_S_values or None
+    o.want_hist = int(bool(want_hist))
     if portfolio_threshold is not None:
         o.want_portfolio = 1
         o.portfolio_loss_threshold = float(portfolio_threshold)
@@ -113,11 +115,11 @@ class Engine:
         return A
 
     def run(self, M, seed, x, k, path_offset=0, kernel=KERNEL_AUTO, no_recheck=False, portfolio_threshold=None,
-            weights=None) -> RunResult:
+            weights=None, want_hist=False) -> RunResult:
         """portfolio_threshold=x_p additionally reduces the portfolio return w.R (weights default 1/N):
         result.portfolio = {hits = #{w.R < -x_p}, mean, var, tail_loss_sum, hist..., VaR{alpha}, ES{alpha}}."""
         r = Result()
-        o = make_options(kernel, no_recheck, portfolio_threshold=portfolio_threshold)
+        o = make_options(kernel, no_recheck, portfolio_threshold=portfolio_threshold, want_hist=want_hist)
         if weights is not None:
             w = _f64(weights)
             check(self._lib.mcr_set_portfolio_weights(self._h, w.ctypes.data, w.shape[0]))
@@ -125,6 +127,8 @@ class Engine:
         res = RunResult.from_c(r)
         if portfolio_threshold is not None:
             res.portfolio = portfolio_outputs(r)
+        if want_hist:
+            res.hist_S = np.ctypeslib.as_array(r.hist_S)[: self.N + 1].astype(np.int64)
         return res
 
     def run_async(self, M, seed, x, k, d_partials_ptr, stream_ptr, path_offset=0, kernel=KERNEL_AUTO,

@@ -44,7 +44,7 @@ typedef struct mcr_run_options {
     int32_t no_recheck;    /* 0 (default): per-asset decisions within the fp32 error band of the threshold are
                               recomputed in fp64, so results equal the fp64 reference arithmetic on the same
                               normals bit-for-bit.  1: raw fp32 decisions (benchmark ablation). */
-    int32_t want_hist;     /* 1: also fill mcr_result.hist_S */
+    int32_t want_hist;     /* 1: also fill mcr_result.hist_S (mcr_run only; costs one 4-byte store + load per trial) */
     int32_t want_portfolio;/* 1: also reduce the equal-/custom-weight portfolio return (north-star extension) */
     int32_t reserved0;
     double portfolio_loss_threshold; /* x_p: portfolio tail event is  w.R < -x_p  */

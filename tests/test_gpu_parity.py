@@ -269,6 +269,21 @@ def test_portfolio_extension_against_oracle(engine, oracle):
         engine.run(1000, seed, x, k, weights=np.full(N, 1.0 / N))      # restore default weights
 
 
+def test_histogram_of_crash_counts(engine, oracle):
+    """want_hist: hist_S[s] = #{trials : S == s}, for every kernel flavour; exact like S itself."""
+    for N, kernels in ((15, (api.KERNEL_FFMA, api.KERNEL_EXACT)), (50, (api.KERNEL_TENSOR, api.KERNEL_FFMA)), (160, (api.KERNEL_AUTO,))):
+        mu, Sigma, x, k = model(N)
+        A = engine.upload_sigma(mu, Sigma)
+        M = 300000 if N < 100 else 30000
+        Z, _ = engine.dump_normals(M, 5)
+        ro = oracle.run_normals(A, mu, k, x, Z)
+        want = np.bincount(ro["S_values"], minlength=N + 1)
+        for kern in kernels:
+            r = engine.run(M, 5, x, k, kernel=kern, want_hist=True)
+            np.testing.assert_array_equal(r.hist_S, want)
+            assert int(r.hist_S[k:].sum()) == r.count and int((np.arange(N + 1) * r.hist_S).sum()) == r.sum_S
+
+
 def test_kernel_selection(engine):
     mu, Sigma, x, k = model(15)
     engine.upload_sigma(mu, Sigma)
