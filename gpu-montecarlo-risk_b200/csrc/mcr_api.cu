@@ -276,7 +276,7 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
     plan->slab = false;
     plan->rows = e->N + (plan->portfolio ? 1 : 0);
     if (!normals && !plan->portfolio && e->N > tc_max_n() && (want == MCR_KERNEL_AUTO || want == MCR_KERNEL_TENSOR)) {
-        plan->kernel = MCR_KERNEL_TENSOR; plan->slab = true; plan->NT = 128 * slab_count(e->N);
+        plan->kernel = MCR_KERNEL_TENSOR; plan->slab = true; plan->NT = slab_rows() * slab_count(e->N);
         return 0;
     }
     const bool tc_ok = !normals && tc_supported(plan->rows);
@@ -500,7 +500,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             const double gamma = std::ldexp(1.0, -19) * std::max(1.0, kbn / 8.0);
             // sum_j |a_ij||z_j| <= ||a_i||_2 ||z||_2 (Cauchy-Schwarz): the kernel tracks ||z||_2 of the trial
             double cabs = 0, rownorm = 0;
-            for (int i = 128 * t; i < std::min(N, 128 * (t + 1)); ++i) {
+            for (int i = slab_rows() * t; i < std::min(N, slab_rows() * (t + 1)); ++i) {
                 cabs = std::max(cabs, std::fabs(c[i]));
                 double ss = 0;
                 for (int j = 0; j < N; ++j) ss += e->A[(size_t)i * N + j] * e->A[(size_t)i * N + j];

@@ -123,6 +123,7 @@ struct SlabLaunch {
     uint16_t* S_acc;             // [M] running per-trial hit count, bit 15 = flagged
     int32_t first_slab;
 };
+int slab_rows();
 int slab_count(int N);
 int slab_ncols(int N, int t, bool lower);
 size_t slab_image_bytes(int N, bool lower);

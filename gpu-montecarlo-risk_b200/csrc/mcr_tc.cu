@@ -470,9 +470,9 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
 // Large asset counts (N > 128): row slabs.
 //
 // 128 trials x N accumulators do not fit TMEM (512 columns) and the transform does not fit shared memory,
-// so the correlate is done one slab of 128 transform rows at a time: slab t needs the normals of
-// columns [0, ncols_t) only (ncols_t = min(N, 128 (t+1)) for a lower-triangular transform), which the
-// generator simply re-derives from the counter-based stream, and its 128 x 64 transform K-blocks are
+// so the correlate is done one slab of 256 transform rows at a time: slab t needs the normals of
+// columns [0, ncols_t) only (ncols_t = min(N, 256 (t+1)) for a lower-triangular transform), which the
+// generator simply re-derives from the counter-based stream, and its 256 x 64 transform K-blocks are
 // streamed from L2 into the same ring slot as the Z K-block they multiply.  Each launch adds the slab's
 // hit count into a per-trial uint16 (bit 15 = "inside the guard band in some slab"); slab_count_kernel
 // then reduces that array exactly like the single-launch kernels do.  Costs: the normals are generated
@@ -484,12 +484,12 @@ struct TcSlabParams {
     int32_t ncols;        // normal columns this slab multiplies; the constant 1 sits in column ncols
     int32_t kb_count;     // K-blocks = ceil((ncols + 1) / 64)
     float delta_rel, delta_abs;   // scaled guard band = delta_rel * ||z||_2 + delta_abs (Cauchy-Schwarz bound on sum |a||z|)
-    const uint4* B_slab;  // global: kb_count x [hi 16 KB | lo 16 KB], rows x 128 B, pre-swizzled
+    const uint4* B_slab;  // global: kb_count x [hi 32 KB | lo 32 KB], SLAB_ROWS rows x 128 B, pre-swizzled
     uint16_t* S_acc;      // [M] running hit count, bit 15 = flagged
     int32_t first_slab;   // overwrite S_acc instead of accumulating
 };
 
-constexpr int SLAB_ROWS = 128;
+constexpr int SLAB_ROWS = 256;                            // transform rows per slab = UMMA N = TMEM columns of one accumulator region
 constexpr uint32_t SLAB_Z_BYTES = 2 * tc::TILE_M * 128;    // Z K-block: hi + lo
 constexpr uint32_t SLAB_B_BYTES = 2 * SLAB_ROWS * 128;     // B K-block: hi + lo
 constexpr uint32_t SLAB_SLOT_BYTES = SLAB_Z_BYTES + SLAB_B_BYTES;
@@ -503,7 +503,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory"); }
 
 // 16 generator warps: warp w works on trial rows 32 (w % 4) .. +31 (its TMEM lane quadrant) and on columns
-// 16 (w / 4) .. +15 of every K-block while generating, accumulator columns 32 (w / 4) .. +31 in the epilogue.
+// 16 (w / 4) .. +15 of every K-block while generating, accumulator columns 64 (w / 4) .. +63 in the epilogue.
 __global__ void __launch_bounds__(SLAB_THREADS, 1) tc_slab_kernel(const TcSlabParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -513,8 +513,9 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) tc_slab_kernel(const TcSlabPa
     __shared__ uint32_t s_part_S[2][SLAB_KSPLIT][128];
     __shared__ float s_part_band[2][SLAB_KSPLIT][128], s_part_zmax[2][SLAB_KSPLIT][128];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr uint32_t TMEM_COLS = 256;   // two accumulator regions of 128 columns
+    constexpr uint32_t TMEM_COLS = 2 * SLAB_ROWS;   // two accumulator regions of SLAB_ROWS columns: all of TMEM
     constexpr int MMA_WARP = SLAB_GEN_THREADS / 32;
+    constexpr int EPI_COLS = SLAB_ROWS / SLAB_KSPLIT;   // accumulator columns per epilogue thread
 
     if (tid == 0)
         for (int b = 0; b < 2; ++b) { mbar_init(&s_empty[b], 1); mbar_init(&s_done[b], 1); }
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) tc_slab_kernel(const TcSlabPa
                     tc_fence_after();
                     const uint32_t zhi = smem_u32(smem + slot * SLAB_SLOT_BYTES), zlo = zhi + TILE_M * 128;
                     const uint32_t bhi = zhi + SLAB_Z_BYTES, blo = bhi + SLAB_ROWS * 128;
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(n & 1) * 128;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(n & 1) * SLAB_ROWS;
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
                         const uint32_t za = pass == 2 ? zlo : zhi;
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) tc_slab_kernel(const TcSlabPa
         const int row = tid & 127, part = tid >> 7;   // part: K-split index while generating, column quarter in the epilogue
         const uint32_t ring_row = smem_u32(smem) + (uint32_t)(row / 8) * 1024u + (uint32_t)(row % 8) * 128u;
         const uint32_t r7s = (uint32_t)(row % 8) << 4;
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)part * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)part * EPI_COLS;
         const int n_full = p.ncols / 8;
         uint32_t empty_phase = 0, done_phase = 0;
         float prev_zmax = 0.0f;
@@ -571,9 +572,10 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) tc_slab_kernel(const TcSlabPa
             tc_fence_after();
             uint32_t S = 0;
             float band = 3.0e38f;
-            {
+#pragma unroll
+            for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
                 uint32_t v[32];
-                tmem_ld32(taddr + r * 128, v);
+                tmem_ld32(taddr + r * SLAB_ROWS + c0, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -613,7 +615,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) tc_slab_kernel(const TcSlabPa
                     mbar_wait(&s_empty[slot], (empty_phase >> slot) & 1u);
                     empty_phase ^= 1u << slot;
                 }
-                // the slab's transform K-block: 32 KB from the pre-swizzled global image (L2 resident), asynchronous
+                // the slab's transform K-block: 64 KB from the pre-swizzled global image (L2 resident), asynchronous
                 {
                     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.B_slab) + (size_t)kb * SLAB_B_BYTES;
                     const uint32_t dst = smem_u32(smem + slot * SLAB_SLOT_BYTES + SLAB_Z_BYTES);
@@ -832,6 +834,7 @@ cudaError_t tc_launch(int N, int rows, const TcLaunch& l, int grid, cudaStream_t
 }
 
 // ---- slab path host side ---------------------------------------------------------------------------------
+int slab_rows() { return SLAB_ROWS; }
 int slab_count(int N) { return (N + SLAB_ROWS - 1) / SLAB_ROWS; }
 int slab_ncols(int N, int t, bool lower) { return lower ? std::min(N, SLAB_ROWS * (t + 1)) : N; }
 int slab_kblocks(int ncols) { return (ncols + 1 + tc::KBLOCK - 1) / tc::KBLOCK; }
