@@ -35,8 +35,6 @@ namespace tc {
 
 constexpr int TILE_M = 128;        // trials per tile = UMMA M = TMEM lanes
 constexpr int KBLOCK = 64;         // fp16 elements per 128-byte swizzle row
-constexpr int GEN_THREADS = 128;   // warps 0..3: generator + epilogue (warp w owns TMEM lanes 32w..32w+31)
-constexpr int THREADS = GEN_THREADS + 32;  // + warp 4: TMEM allocation and MMA issue
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -44,16 +42,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+#ifndef MCR_MBAR_SLEEP_NS
+#define MCR_MBAR_SLEEP_NS 0   // back-off between failed polls (0: poll again at once)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
         "WAIT_LOOP:\n"
+#if MCR_MBAR_SLEEP_NS > 0
+        "nanosleep.u32 %2;\n"
+#endif
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE;\n"
         "bra WAIT_LOOP;\n"
         "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)MCR_MBAR_SLEEP_NS) : "memory");
 }
 
 // ---- tcgen05 wrappers ------------------------------------------------------------------------------
@@ -152,7 +158,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile
 #define MCR_TC_ABLATE 0
 #endif
 #ifndef MCR_TC_GROUPS
-#define MCR_TC_GROUPS 3   // generator warpgroups per CTA while 2 accumulator regions per group fit TMEM (NOUT <= 64)
+#define MCR_TC_GROUPS 6   // warpgroups per CTA where TMEM and shared memory allow (768 threads: 80 registers each, no spills)
 #endif
 #ifndef MCR_TC_UNROLL
 #define MCR_TC_UNROLL 2
@@ -200,37 +206,43 @@ __device__ __forceinline__ void store_chunk(const float (&z)[8], int c8, uint32_
 
 // NOUT   = transform rows padded to a multiple of 16 (UMMA N)
 // KB     = 64-column K-blocks (K = N + 1 padded)
-// GROUPS = generator warpgroups per CTA.
+// GROUPS = warpgroups per CTA (one CTA per SM; the groups are what fills the SM).
 //
-// Pipeline (per group; the single MMA warp serves the groups round-robin):
-//   * Z is produced one K-block (128 trials x 64 columns, fp16 hi + lo = 32 KB) at a time into a ring of
-//     two shared-memory slots; a slot is handed to the MMA warp through a named barrier ("full") and
-//     comes back through an mbarrier the MMA warp commits to ("empty").  Shared memory per group is
-//     therefore 64 KB whatever K is.
-//   * every tile accumulates into one of two TMEM regions of the group; the MMA warp commits to a
-//     "done" mbarrier after the tile's last K-block.
-//   * the epilogue of tile n runs AFTER the group has generated tile n+1, so it never waits for the
-//     tensor core in steady state: the generator warps issue Philox/Box-Muller work back to back.
+// Every warpgroup (128 threads = the 128 trials of a tile) is a self-contained pipeline; the groups share
+// only the resident transform image:
+//   * the group owns ONE shared-memory slot (a K-block of Z: 128 trials x 64 columns, fp16 hi + lo =
+//     32 KB), ONE TMEM accumulator region and ONE mbarrier.  K-block u of the group is generated into the
+//     slot, handed over through a named barrier of the group's 128 threads, and one warp of the group
+//     (warp u % 4, so the extra work rotates) issues its MMAs and commits them to the mbarrier: phase u
+//     of the mbarrier completes when the tensor core has finished K-blocks 0..u.
+//   * before the first store of K-block u + 1 the threads wait for phase u (the slot is free again and,
+//     when u closed a tile, the tile's accumulator is complete).  The wait comes after the first batch of
+//     Philox / Box-Muller work of that K-block, and the MMAs of a K-block take a few hundred cycles, so
+//     it does not stall in steady state.
+//   * the epilogue of tile n runs after K-block 0 of tile n + 1 has been generated and before that
+//     K-block's hand-over barrier: everyone has read the accumulator region before the MMA that
+//     overwrites it is issued, so a single region per group is enough.
+// No group ever waits for another one (an earlier version served all groups from one MMA warp in
+// round-robin order: about 10 % of the warp samples sat in that coupling).
 template <int NOUT, int KB, int GROUPS>
-__global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcParams p) {
+__global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams p) {
     using namespace tc;
     constexpr uint32_t SLOT_BYTES = 2 * TILE_M * 128;   // one K-block of Z: hi then lo
     constexpr uint32_t B_BYTES = KB * NOUT * 128;       // one of Bhi / Blo
     constexpr uint32_t GROUP_COLS = (NOUT + 31) & ~31;  // TMEM columns of one accumulator region
-    constexpr uint32_t NEED_COLS = 2 * GROUP_COLS * GROUPS;
+    constexpr uint32_t NEED_COLS = GROUP_COLS * GROUPS;
     constexpr uint32_t TMEM_COLS = NEED_COLS <= 32 ? 32 : NEED_COLS <= 64 ? 64 : NEED_COLS <= 128 ? 128 : NEED_COLS <= 256 ? 256 : 512;
     static_assert(NEED_COLS <= 512, "accumulators do not fit TMEM");
-    constexpr int NTHREADS = 128 * GROUPS + 32;
-    constexpr int MMA_WARP = 4 * GROUPS;
+    constexpr int NTHREADS = 128 * GROUPS;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* s_ring = smem;                                   // [group][slot][hi|lo][128 x 128 B]
-    uint8_t* s_bhi = smem + 2 * GROUPS * SLOT_BYTES;
+    uint8_t* s_ring = smem;                                   // [group][hi|lo][128 x 128 B]
+    uint8_t* s_bhi = smem + GROUPS * SLOT_BYTES;
     uint8_t* s_blo = s_bhi + B_BYTES;
     uint32_t* s_hist_cnt = reinterpret_cast<uint32_t*>(s_blo + B_BYTES);          // only when p.portfolio (host sizes smem)
     float* s_hist_sum = reinterpret_cast<float*>(s_hist_cnt + PORT_BINS);
-    __shared__ uint64_t s_empty[GROUPS][2], s_done[GROUPS][2];
+    __shared__ uint64_t s_mma[GROUPS];
     __shared__ double s_port[4 * GROUPS][4];
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_cnt[4 * GROUPS], s_sum[4 * GROUPS];
@@ -246,9 +258,8 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
     if (p.portfolio)
         for (uint32_t t = tid; t < PORT_BINS; t += NTHREADS) { s_hist_cnt[t] = 0u; s_hist_sum[t] = 0.0f; }
     if (tid == 0)
-        for (int gg = 0; gg < GROUPS; ++gg)
-            for (int b = 0; b < 2; ++b) { mbar_init(&s_empty[gg][b], 1); mbar_init(&s_done[gg][b], 1); }
-    if (warp == MMA_WARP) tmem_alloc(&s_tmem, TMEM_COLS);
+        for (int gg = 0; gg < GROUPS; ++gg) mbar_init(&s_mma[gg], 1);
+    if (warp == 0) tmem_alloc(&s_tmem, TMEM_COLS);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -263,70 +274,31 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
     uint32_t p_hits = 0;
     float p_sum = 0.f, p_sum2 = 0.f, p_tail = 0.f;
 
-    if (warp == MMA_WARP) {
-        // ---- MMA warp: K-block u of group g, round-robin over g, in the order the groups produce them ----
-        uint64_t group_tiles[GROUPS];
-        uint64_t max_tiles = 0;
-#pragma unroll
-        for (int g = 0; g < GROUPS; ++g) {
-            group_tiles[g] = cta_tiles > (uint64_t)g ? (cta_tiles - g + GROUPS - 1) / GROUPS : 0;
-            max_tiles = group_tiles[g] > max_tiles ? group_tiles[g] : max_tiles;
-        }
-        const uint32_t bhi = smem_u32(s_bhi), blo = smem_u32(s_blo);
-        for (uint64_t n = 0; n < max_tiles; ++n) {
-#pragma unroll 1
-            for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-                for (int g = 0; g < GROUPS; ++g) {
-                    if (n >= group_tiles[g]) continue;
-                    const uint32_t u = (uint32_t)(n * KB + kb), slot = u & 1;
-                    named_bar_sync(1 + 2 * g + slot, 160);   // the slot is full and visible to the async proxy
-                    if (lane == 0) {
-                        tc_fence_after();
-                        const uint32_t zhi = smem_u32(s_ring + (2 * g + slot) * SLOT_BYTES), zlo = zhi + TILE_M * 128;
-                        const uint32_t d_tmem = tmem_base + (2 * g + (uint32_t)(n & 1)) * GROUP_COLS;
-#pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
-                            const uint32_t za = pass == 2 ? zlo : zhi;
-                            const uint32_t ba = (pass == 1 ? blo : bhi) + kb * (NOUT * 128);
-#pragma unroll
-                            for (int ks = 0; ks < (MCR_TC_ABLATE == 3 ? 0 : KBLOCK / 16); ++ks)
-                                umma_f16(d_tmem, make_desc(za + ks * 32), make_desc(ba + ks * 32), IDESC,
-                                         (kb | pass | ks) != 0 ? 1u : 0u);
-                        }
-                        umma_commit(&s_empty[g][slot]);                  // slot may be overwritten once these MMAs are done
-                        if (kb == KB - 1) umma_commit(&s_done[g][n & 1]); // ... and the tile's accumulator is complete
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-    } else {
-        // ---- generator + epilogue warps ----
-        const int g = warp / 4;
+    {
+        const int g = warp / 4, wg = warp % 4;
         const int row = tid - 128 * g;
-        const uint32_t ring_row = smem_u32(s_ring + 2 * g * SLOT_BYTES) + (uint32_t)(row / 8) * 1024u + (uint32_t)(row % 8) * 128u;
+        uint64_t* const bar = &s_mma[g];
+        const uint32_t slot_base = smem_u32(s_ring + g * SLOT_BYTES);
+        const uint32_t zhi_row = slot_base + (uint32_t)(row / 8) * 1024u + (uint32_t)(row % 8) * 128u, zlo_row = zhi_row + TILE_M * 128;
         const uint32_t r7s = (uint32_t)(row % 8) << 4;
-        const uint32_t taddr_g = tmem_base + 2 * g * GROUP_COLS + ((uint32_t)((warp % 4) * 32) << 16);
+        const uint32_t d_tmem = tmem_base + g * GROUP_COLS;
+        const uint32_t taddr = d_tmem + ((uint32_t)(wg * 32) << 16);
+        const uint32_t bhi = smem_u32(s_bhi), blo = smem_u32(s_blo);
         const uint64_t my_tiles = cta_tiles > (uint64_t)g ? (cta_tiles - g + GROUPS - 1) / GROUPS : 0;
         const int n_full = p.N / 8;       // chunks (8 columns) made of normals only
-        uint32_t empty_phase = 0;         // bit s: parity to wait for on s_empty[g][s]
-        uint32_t done_phase = 0;          // bit r: parity to wait for on s_done[g][r]
         float prev_zmax = 0.0f;
         uint64_t prev_i = 0;
+        uint32_t u = 0;                   // K-blocks this group has produced so far
 
-        // epilogue of local tile n (accumulator region n & 1): TMEM -> registers, threshold + guard band
-        auto epilogue = [&](uint64_t n, uint64_t i, float zmax) {
-            const uint32_t r = (uint32_t)(n & 1);
-            mbar_wait(&s_done[g][r], (done_phase >> r) & 1u);
-            done_phase ^= 1u << r;
+        // epilogue of a finished tile: TMEM -> registers, threshold + guard band
+        auto epilogue = [&](uint64_t i, float zmax) {
             tc_fence_after();
             uint32_t S = 0;
             float band = 3.0e38f;
 #pragma unroll
             for (int c0 = 0; c0 < (MCR_TC_ABLATE == 2 ? 0 : NOUT); c0 += 32) {
                 uint32_t v[32];
-                tmem_ld32(taddr_g + r * GROUP_COLS + c0, v);
+                tmem_ld32(taddr + c0, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -354,7 +326,6 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
                     }
                 }
             }
-            tc_fence_before();
             if (i < p.M) {
                 if (band < __fmaf_rn(p.delta_rel, zmax, p.delta_abs)) {
                     const uint32_t slot = atomicAdd(p.flag_count, 1u);
@@ -375,19 +346,19 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
             rng.init((uint32_t)path, (uint32_t)(path >> 32), p.key1);
             float zmax = 0.0f;
 #pragma unroll 1
-            for (int kb = 0; kb < KB; ++kb) {
-                const uint32_t u = (uint32_t)(n * KB + kb), slot = u & 1;
-                if (u >= 2) {   // wait until the MMAs that read this slot two K-blocks ago have completed
-                    mbar_wait(&s_empty[g][slot], (empty_phase >> slot) & 1u);
-                    empty_phase ^= 1u << slot;
-                }
-                const uint32_t zhi_row = ring_row + slot * SLOT_BYTES, zlo_row = zhi_row + TILE_M * 128;
+            for (int kb = 0; kb < KB; ++kb, ++u) {
+                // the slot may be overwritten once the MMAs of the previous K-block have completed (phase u - 1)
+                bool slot_free = (u == 0);
+                auto acquire = [&]() {
+                    if (!slot_free) { mbar_wait(bar, (u - 1) & 1u); slot_free = true; }
+                };
                 // chunks 8*kb .. 8*kb+7 of the row: normals, then the constant 1 in column N, zeros beyond
                 const int c_begin = 8 * kb;
                 int c8 = c_begin;
                 for (; c8 + TC_UNROLL <= min(n_full, c_begin + 8); c8 += TC_UNROLL) {
                     float z[8 * TC_UNROLL];
                     rng.normals_multi<2 * TC_UNROLL>((uint32_t)(2 * c8), p.key0, p.key1, z);
+                    acquire();
 #pragma unroll
                     for (int w = 0; w < TC_UNROLL; ++w) {
                         float zc[8];
@@ -399,8 +370,10 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
                 for (; c8 < min(n_full, c_begin + 8); ++c8) {
                     float z[8];
                     rng.normals_multi<2>((uint32_t)(2 * c8), p.key0, p.key1, z);
+                    acquire();
                     store_chunk(z, c8 - c_begin, zhi_row, zlo_row, r7s, zmax);
                 }
+                acquire();
                 for (; c8 < c_begin + 8; ++c8) {   // at most 8 such chunks per tile: the one holding column N, then zeros
                     float z[8];
 #pragma unroll
@@ -418,15 +391,37 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
                     }
                     store_chunk(z, c8 - c_begin, zhi_row, zlo_row, r7s, zmax_unused);
                 }
-                fence_async_smem();                      // generic-proxy smem writes -> visible to the tensor core
-                if (kb == 0) tc_fence_before();          // this tile's first MMA overwrites a TMEM region we read earlier
-                named_bar_arrive(1 + 2 * g + slot, 160);  // hand the K-block to the MMA warp (no wait)
+                // phase u - 1 is complete here; when it closed tile n - 1, that tile's accumulator is final
+                if (kb == 0 && n > 0) epilogue(prev_i, prev_zmax);
+                fence_async_smem();     // generic-proxy smem writes -> visible to the tensor core
+                tc_fence_before();      // our TMEM reads are ordered before the hand-over
+                if (wg == (int)(u & 3u)) {
+                    named_bar_sync(1 + g, 128);   // the K-block is complete and everyone is done with the accumulator
+                    if (lane == 0) {
+                        tc_fence_after();
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t za = pass == 2 ? slot_base + TILE_M * 128 : slot_base;
+                            const uint32_t ba = (pass == 1 ? blo : bhi) + kb * (NOUT * 128);
+#pragma unroll
+                            for (int ks = 0; ks < (MCR_TC_ABLATE == 3 ? 0 : KBLOCK / 16); ++ks)
+                                umma_f16(d_tmem, make_desc(za + ks * 32), make_desc(ba + ks * 32), IDESC,
+                                         (kb | pass | ks) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(bar);
+                    }
+                    __syncwarp();
+                } else {
+                    named_bar_arrive(1 + g, 128);
+                }
             }
-            if (n > 0) epilogue(n - 1, prev_i, prev_zmax);   // tile n-1 finished long ago: no stall in steady state
             prev_i = i;
             prev_zmax = zmax;
         }
-        if (my_tiles > 0) epilogue(my_tiles - 1, prev_i, prev_zmax);
+        if (my_tiles > 0) {
+            mbar_wait(bar, (u - 1) & 1u);
+            epilogue(prev_i, prev_zmax);
+        }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         sum_s = __reduce_add_sync(0xffffffffu, sum_s);
         if (lane == 0) { s_cnt[warp] = cnt; s_sum[warp] = sum_s; }
@@ -463,7 +458,7 @@ __global__ void __launch_bounds__(128 * GROUPS + 32, 1) tc_path_kernel(const TcP
             }
         }
     }
-    if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // ======================================================================================================
@@ -727,7 +722,7 @@ static void tc_build_image(const double* A, const double* c, int N, const double
 
 template <int NOUT, int KB, int GROUPS>
 static size_t tc_smem_bytes(bool portfolio) {
-    return 2 * (size_t)GROUPS * 2 * tc::TILE_M * 128 + 2 * (size_t)KB * NOUT * 128 + 1024 + (portfolio ? 8 * (size_t)PORT_BINS : 0);
+    return (size_t)GROUPS * 2 * tc::TILE_M * 128 + 2 * (size_t)KB * NOUT * 128 + 1024 + (portfolio ? 8 * (size_t)PORT_BINS : 0);
 }
 
 template <int NOUT, int KB, int GROUPS>
@@ -744,7 +739,7 @@ template <int NOUT, int KB, int GROUPS>
 static cudaError_t tc_launch_impl(const TcParams& p, int grid, cudaStream_t s) {
     cudaError_t e = tc_prepare<NOUT, KB, GROUPS>(p.portfolio != 0);
     if (e != cudaSuccess) return e;
-    tc_path_kernel<NOUT, KB, GROUPS><<<grid, 128 * GROUPS + 32, tc_smem_bytes<NOUT, KB, GROUPS>(p.portfolio != 0), s>>>(p);
+    tc_path_kernel<NOUT, KB, GROUPS><<<grid, 128 * GROUPS, tc_smem_bytes<NOUT, KB, GROUPS>(p.portfolio != 0), s>>>(p);
     return cudaGetLastError();
 }
 
@@ -763,8 +758,8 @@ static cudaError_t tc_occupancy_impl(int* bps, bool portfolio) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
-    constexpr int threads = 128 * GROUPS + 32;
-    constexpr uint32_t group_cols = (NOUT + 31) & ~31, need = 2 * group_cols * GROUPS;
+    constexpr int threads = 128 * GROUPS;
+    constexpr uint32_t group_cols = (NOUT + 31) & ~31, need = group_cols * GROUPS;
     constexpr int tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
     const size_t per_cta = tc_smem_bytes<NOUT, KB, GROUPS>(portfolio) + fa.sharedSizeBytes + 1024;  // + driver reservation
     int n = (int)(smem_sm / per_cta);
@@ -792,12 +787,21 @@ static TcVariant tc_variant() {
                      &tc_occupancy_impl<NOUT, KB, GROUPS>};
 }
 
+// warpgroups per CTA: as many as the tuning default, TMEM (512 columns) and shared memory (227 KB) allow
+constexpr int tc_groups(int nout, int kb) {
+    int g = MCR_TC_GROUPS;
+    const int cols = (nout + 31) & ~31;
+    while (g > 1 && (g * cols > 512 || g * 32768 + 2 * kb * nout * 128 + 4096 > 227 * 1024)) --g;
+    return g;
+}
+
 // smallest instantiation with nout >= N and 64 * kb >= N + 1
 static const TcVariant* tc_find(int N) {
     static const TcVariant table[] = {
-        tc_variant<16, 1, MCR_TC_GROUPS>(), tc_variant<32, 1, MCR_TC_GROUPS>(), tc_variant<48, 1, MCR_TC_GROUPS>(),
-        tc_variant<64, 1, MCR_TC_GROUPS>(), tc_variant<64, 2, MCR_TC_GROUPS>(), tc_variant<80, 2, (MCR_TC_GROUPS < 2 ? MCR_TC_GROUPS : 2)>(),
-        tc_variant<96, 2, (MCR_TC_GROUPS < 2 ? MCR_TC_GROUPS : 2)>(), tc_variant<112, 2, 2>(), tc_variant<128, 2, 2>(), tc_variant<128, 3, 2>(),
+        tc_variant<16, 1, tc_groups(16, 1)>(), tc_variant<32, 1, tc_groups(32, 1)>(), tc_variant<48, 1, tc_groups(48, 1)>(),
+        tc_variant<64, 1, tc_groups(64, 1)>(), tc_variant<64, 2, tc_groups(64, 2)>(), tc_variant<80, 2, tc_groups(80, 2)>(),
+        tc_variant<96, 2, tc_groups(96, 2)>(), tc_variant<112, 2, tc_groups(112, 2)>(), tc_variant<128, 2, tc_groups(128, 2)>(),
+        tc_variant<128, 3, tc_groups(128, 3)>(),
     };
     for (const TcVariant& v : table)
         if (v.nout >= N && 64 * v.kb >= N + 1) return &v;
