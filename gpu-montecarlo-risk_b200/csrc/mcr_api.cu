@@ -173,6 +173,7 @@ int mcr_destroy(mcr_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_mu); cudaFree(e->d_Acm); cudaFree(e->d_tc_image); cudaFree(e->d_slab_image); cudaFree(e->d_S_acc);
+    cudaFree(e->d_pair_list); cudaFree(e->d_pair_count); cudaFree(e->d_Arm);
     cudaFree(e->d_flag_list); cudaFree(e->d_flag_count); cudaFree(e->d_accum);
     cudaFree(e->d_block_partials); cudaFree(e->d_partials);
     cudaFree(e->d_port_acc); cudaFree(e->d_port_hist); cudaFree(e->d_port_hist_sum);
@@ -208,8 +209,8 @@ int mcr_upload_model(mcr_engine* e, int N, const double* mu, const double* A, in
     e->gen = g_next_gen.fetch_add(1);
     // fp64 copies for the exact / fix-up kernel (A column-major)
     if (N != e->N_alloc) {
-        cudaFree(e->d_mu); cudaFree(e->d_Acm);
-        e->d_mu = nullptr; e->d_Acm = nullptr; e->N_alloc = 0;
+        cudaFree(e->d_mu); cudaFree(e->d_Acm); cudaFree(e->d_Arm);
+        e->d_mu = nullptr; e->d_Acm = nullptr; e->d_Arm = nullptr; e->Arm_gen = 0; e->N_alloc = 0;
         MCR_CUDA(cudaMalloc(&e->d_mu, sizeof(double) * N));
         MCR_CUDA(cudaMalloc(&e->d_Acm, sizeof(double) * (size_t)N * N));
         e->N_alloc = N;
@@ -481,6 +482,14 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             e->slab_image_cap = bytes; e->slab_gen = 0;
         }
         if (!e->d_S_acc) MCR_CUDA(cudaMalloc(&e->d_S_acc, sizeof(uint16_t) * SLAB_CHUNK_PATHS));
+        if (!e->d_pair_list) MCR_CUDA(cudaMalloc(&e->d_pair_list, sizeof(unsigned long long) * PAIR_CAP));
+        if (!e->d_pair_count) MCR_CUDA(cudaMalloc(&e->d_pair_count, sizeof(uint32_t)));
+        if (!e->d_Arm) MCR_CUDA(cudaMalloc(&e->d_Arm, sizeof(double) * (size_t)N * N));
+        if (e->Arm_gen != e->gen) {
+            MCR_CUDA(cudaStreamSynchronize(s));
+            MCR_CUDA(cudaMemcpyAsync(e->d_Arm, e->A.data(), sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, s));
+            e->Arm_gen = e->gen;
+        }
         std::vector<double> c(N);
         for (int i = 0; i < N; ++i) c[i] = e->mu[i] + x;
         if (e->slab_gen != e->gen || e->slab_x != x) {
@@ -516,6 +525,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         if (m == 0) break;
         MCR_CUDA(cudaMemsetAsync(e->d_accum, 0, sizeof(unsigned long long) * 2, s));
         MCR_CUDA(cudaMemsetAsync(e->d_flag_count, 0, sizeof(uint32_t), s));
+        if (plan.slab) MCR_CUDA(cudaMemsetAsync(e->d_pair_count, 0, sizeof(uint32_t), s));
         FinalizeParams fin{};
         fin.M = m; fin.out = d_out; fin.accum = e->d_accum;
         ExactParams xp{};
@@ -534,10 +544,20 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
                 sl.delta_rel = slab_drel[t]; sl.delta_abs = slab_dabs[t];
                 sl.d_slab_image = (const uint8_t*)e->d_slab_image + e->slab_offsets[t];
                 sl.S_acc = e->d_S_acc; sl.first_slab = t == 0;
+                sl.row_base = slab_rows() * t;
+                sl.pair_list = plan.recheck ? e->d_pair_list : nullptr; sl.pair_count = e->d_pair_count; sl.pair_cap = PAIR_CAP;
                 const bool timed = e->n_timed < MAX_TIMED_CHUNKS;
                 if (timed) MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed], s));
                 MCR_CUDA(slab_launch(sl, e->num_sms, s));
                 if (timed) { MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed + 1], s)); ++e->n_timed; }
+                ++launches;
+            }
+            if (plan.recheck) {   // single near-threshold decisions: one fp64 row each, added to S_acc before it is counted
+                PairParams pp{};
+                pp.pair_list = e->d_pair_list; pp.pair_count = e->d_pair_count; pp.pair_cap = PAIR_CAP;
+                pp.path_offset = path_offset + done; pp.key0 = key0; pp.key1 = key1;
+                pp.N = N; pp.lower = e->lower ? 1 : 0; pp.x = x; pp.mu = e->d_mu; pp.A_rm = e->d_Arm; pp.S_acc = e->d_S_acc;
+                MCR_CUDA(launch_exact_pairs(pp, e->num_sms, s));
                 ++launches;
             }
             const int grid = (int)std::min<uint64_t>((uint64_t)std::min(e->num_sms * 8, MAX_GRID), (m + 255) / 256);
@@ -550,6 +570,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             }
             fin.block_partials = e->d_block_partials; fin.n_blocks = grid;
             fin.flag_count = e->d_flag_count; fin.flag_cap = FLAG_CAP;
+            if (plan.recheck) { fin.pair_count = e->d_pair_count; fin.pair_cap = PAIR_CAP; }
         } else if (plan.kernel == MCR_KERNEL_TENSOR) {
             tl.M = m; tl.path_offset = path_offset + done; tl.S_out = xp.S_out;
             const uint64_t tiles = (m + 127) / 128;

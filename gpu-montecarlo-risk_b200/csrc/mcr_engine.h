@@ -9,6 +9,7 @@ namespace mcr {
 constexpr uint64_t CHUNK_PATHS = 1ull << 27;   // trials per launch of the path kernel
 constexpr uint64_t SLAB_CHUNK_PATHS = 1ull << 24;  // trials per chunk on the row-slab path (uint16 accumulator per trial)
 constexpr uint32_t FLAG_CAP = 1u << 22;        // fix-up list entries per chunk (3.1 % of a chunk)
+constexpr uint32_t PAIR_CAP = 1u << 22;        // slab path: single (trial, row) fix-ups per chunk of 2^24 trials
 constexpr int MAX_GRID = 148 * 16 * 2;
 constexpr int MAX_TIMED_CHUNKS = 16;
 int fail(const char* fmt, ...);
@@ -51,6 +52,10 @@ struct mcr_engine {
     std::vector<uint8_t> slab_host_image;
     std::vector<size_t> slab_offsets;
     uint16_t* d_S_acc = nullptr;
+    unsigned long long* d_pair_list = nullptr;   // single near-threshold (trial, row) decisions of a chunk
+    uint32_t* d_pair_count = nullptr;
+    double* d_Arm = nullptr;                     // fp64 transform, row-major (per-decision fix-up)
+    uint64_t Arm_gen = 0;
     double gamma_rowabs_max = 0;  // max_i gamma_i * sum_j |A_ij|
     // scratch
     uint32_t* d_flag_list = nullptr;

@@ -85,7 +85,176 @@ __global__ void __launch_bounds__(EXACT_WARPS * 32) exact_kernel(const ExactPara
     }
 }
 
+// Blocked flavour for N > 128.  The warp-per-trial kernel above streams the whole transform (N^2 * 4..8 bytes,
+// far more than L1) once per trial and ends up bound by L2 bandwidth.  Here a block takes EXB_T trials at a
+// time, keeps their normals in shared memory ([column][trial], so one broadcast LDS.128 feeds two trials)
+// and every thread carries two rows x EXB_T independent fp64 chains: each transform element loaded is
+// used EXB_T times and the FP64 pipe never waits on a dependent add.  Per row the arithmetic and its order
+// are exactly the ones above.
+#ifndef MCR_EXB_T
+#define MCR_EXB_T 8
+#endif
+#ifndef MCR_EXB_MINB
+#define MCR_EXB_MINB 4
+#endif
+constexpr int EXB_THREADS = 128, EXB_T = MCR_EXB_T;
+
+__device__ __forceinline__ void exb_step(double (&acc)[EXB_T], const double a, const double* __restrict__ zj) {
+#pragma unroll
+    for (int q = 0; q < EXB_T; q += 2) {
+        const double2 z = *reinterpret_cast<const double2*>(zj + q);
+        acc[q] = __dadd_rn(acc[q], __dmul_rn(z.x, a));
+        acc[q + 1] = __dadd_rn(acc[q + 1], __dmul_rn(z.y, a));
+    }
+}
+
+// columns [j0, j1) of ROWS (1 or 2) rows, 128 apart; transform elements are fetched EXB_AHEAD columns at a
+// time, one batch ahead of the arithmetic, so the L2 latency of the loads is covered by the batch in flight
+constexpr int EXB_AHEAD = 4;
+template <int ROWS>
+__device__ __forceinline__ void exb_span(double (&acc0)[EXB_T], double (&acc1)[EXB_T], const double* __restrict__ a, int N,
+                                         int j0, int j1, const double* __restrict__ s_zt) {
+    double cur[ROWS][EXB_AHEAD], nxt[ROWS][EXB_AHEAD];
+    const int n_batches = (j1 - j0) / EXB_AHEAD;
+    auto fetch = [&](double (&buf)[ROWS][EXB_AHEAD], int j) {
+#pragma unroll
+        for (int u = 0; u < EXB_AHEAD; ++u) {
+            buf[0][u] = __ldg(a + (size_t)(j + u) * N);
+            if (ROWS == 2) buf[ROWS - 1][u] = __ldg(a + (size_t)(j + u) * N + EXB_THREADS);
+        }
+    };
+    if (n_batches > 0) fetch(cur, j0);
+    int j = j0;
+    for (int b = 0; b < n_batches; ++b, j += EXB_AHEAD) {
+        if (b + 1 < n_batches) fetch(nxt, j + EXB_AHEAD);
+#pragma unroll
+        for (int u = 0; u < EXB_AHEAD; ++u) {
+            exb_step(acc0, cur[0][u], s_zt + (j + u) * EXB_T);
+            if (ROWS == 2) exb_step(acc1, cur[ROWS - 1][u], s_zt + (j + u) * EXB_T);
+        }
+#pragma unroll
+        for (int u = 0; u < EXB_AHEAD; ++u) {
+            cur[0][u] = nxt[0][u];
+            if (ROWS == 2) cur[ROWS - 1][u] = nxt[ROWS - 1][u];
+        }
+    }
+    for (; j < j1; ++j) {
+        exb_step(acc0, __ldg(a + (size_t)j * N), s_zt + j * EXB_T);
+        if (ROWS == 2) exb_step(acc1, __ldg(a + (size_t)j * N + EXB_THREADS), s_zt + j * EXB_T);
+    }
+}
+
+__global__ void __launch_bounds__(EXB_THREADS, MCR_EXB_MINB) exact_block_kernel(const ExactParams p) {
+    extern __shared__ __align__(16) double s_zt[];   // [N][EXB_T]
+    __shared__ int s_S[EXB_T];
+    __shared__ uint64_t s_idx[EXB_T];
+    constexpr uint64_t NONE = ~0ull;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int N = p.N;
+
+    uint64_t n_items = p.M;
+    if (p.flag_list) {
+        const uint32_t c = *p.flag_count;
+        n_items = c < p.flag_cap ? c : p.flag_cap;
+    }
+    const uint64_t n_groups = (n_items + EXB_T - 1) / EXB_T;
+    const double neg_x = -p.x;
+
+    for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        if (tid < EXB_T) {
+            const uint64_t item = grp * EXB_T + tid;
+            s_idx[tid] = item < n_items ? (p.flag_list ? (uint64_t)p.flag_list[item] : item) : NONE;
+            s_S[tid] = 0;
+        }
+        __syncthreads();
+        if (p.Z) {
+            for (int e = tid; e < EXB_T * N; e += EXB_THREADS) {
+                const int q = e / N, j = e - q * N;
+                const uint64_t i = s_idx[q];
+                s_zt[j * EXB_T + q] = i != NONE ? p.Z[i * (uint64_t)N + j] : 0.0;
+            }
+        } else {
+            const int nb = (N + 3) / 4;
+            for (int e = tid; e < EXB_T * nb; e += EXB_THREADS) {
+                const int q = e / nb, b = e - q * nb;
+                const uint64_t i = s_idx[q];
+                float zf[4] = {0.f, 0.f, 0.f, 0.f};
+                if (i != NONE) {
+                    const uint64_t path = p.path_offset + i;
+                    normals4((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)b, p.key0, p.key1, zf);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (4 * b + c < N) s_zt[(4 * b + c) * EXB_T + q] = (double)zf[c];
+            }
+        }
+        __syncthreads();
+
+        int hits[EXB_T];
+#pragma unroll
+        for (int q = 0; q < EXB_T; ++q) hits[q] = 0;
+        for (int rA = tid; rA < N; rA += 2 * EXB_THREADS) {
+            const int rB = rA + EXB_THREADS;
+            const int jendA = p.lower ? rA + 1 : N;
+            const int jendB = rB < N ? (p.lower ? rB + 1 : N) : 0;
+            double accA[EXB_T], accB[EXB_T];
+#pragma unroll
+            for (int q = 0; q < EXB_T; ++q) { accA[q] = 0.0; accB[q] = 0.0; }
+            const double* a = p.A_cm + rA;
+            if (rB < N) {
+                exb_span<2>(accA, accB, a, N, 0, jendA, s_zt);                       // both rows
+                exb_span<1>(accB, accA, a + EXB_THREADS, N, jendA, jendB, s_zt);     // columns only row B has
+            } else {
+                exb_span<1>(accA, accB, a, N, 0, jendA, s_zt);
+            }
+            const double muA = p.mu[rA], muB = rB < N ? p.mu[rB] : 0.0;
+#pragma unroll
+            for (int q = 0; q < EXB_T; ++q) {
+                double R = __dadd_rn(__dadd_rn(0.0, __dmul_rn(1.0, accA[q])), muA);
+                hits[q] += (R < neg_x) ? 1 : 0;
+                if (rB < N) {
+                    R = __dadd_rn(__dadd_rn(0.0, __dmul_rn(1.0, accB[q])), muB);
+                    hits[q] += (R < neg_x) ? 1 : 0;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < EXB_T; ++q) {
+            const int h = __reduce_add_sync(0xffffffffu, hits[q]);
+            if (lane == 0 && h) atomicAdd(&s_S[q], h);
+        }
+        __syncthreads();
+        if (tid < EXB_T && s_idx[tid] != NONE) {
+            const int S = s_S[tid];
+            if (S >= p.k) atomicAdd(&p.accum[0], 1ull);
+            atomicAdd(&p.accum[1], (unsigned long long)S);
+            if (p.S_out) p.S_out[s_idx[tid]] = S;
+            if (p.hist) atomicAdd(&p.hist[S], 1ull);
+        }
+        __syncthreads();
+    }
+}
+
+#ifndef MCR_EXACT_BLOCK_MIN_N
+#define MCR_EXACT_BLOCK_MIN_N 129
+#endif
+
 cudaError_t launch_exact(const ExactParams& p, int num_sms, cudaStream_t s) {
+    if (p.N >= MCR_EXACT_BLOCK_MIN_N) {
+        const size_t smem = sizeof(double) * (size_t)EXB_T * p.N;
+        cudaError_t e = cudaFuncSetAttribute(exact_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int bps = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, exact_block_kernel, EXB_THREADS, smem);
+        if (e != cudaSuccess) return e;
+        int grid = num_sms * std::max(bps, 1);
+        if (!p.flag_list) {
+            const uint64_t need = (p.M + EXB_T - 1) / EXB_T;
+            if (need < (uint64_t)grid) grid = (int)(need ? need : 1);
+        }
+        exact_block_kernel<<<grid, EXB_THREADS, smem, s>>>(p);
+        return cudaGetLastError();
+    }
     const size_t smem = sizeof(double) * (size_t)EXACT_WARPS * p.N;
     int grid = num_sms * 8;
     if (!p.flag_list) {
@@ -93,6 +262,39 @@ cudaError_t launch_exact(const ExactParams& p, int num_sms, cudaStream_t s) {
         if (need < (uint64_t)grid) grid = (int)(need ? need : 1);
     }
     exact_kernel<<<grid, EXACT_WARPS * 32, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ---- single decisions of the slab path ------------------------------------------------------------------------
+// One thread per (trial, row): the trial's normals are re-derived from the counter-based stream in column order
+// and the row's sum is accumulated exactly as in exact_kernel; a hit is added to the trial's uint16 in S_acc.
+__global__ void __launch_bounds__(128) exact_pairs_kernel(const PairParams p) {
+    const uint32_t c = *p.pair_count;
+    const uint32_t n = c < p.pair_cap ? c : p.pair_cap;
+    const double neg_x = -p.x;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const unsigned long long e = p.pair_list[t];
+        const uint64_t i = e >> 16;
+        const int row = (int)(e & 0xFFFFu);
+        const uint64_t path = p.path_offset + i;
+        const int jend = p.lower ? row + 1 : p.N;
+        const double* a = p.A_rm + (size_t)row * p.N;
+        double acc = 0.0;
+        for (int b = 0; 4 * b < jend; ++b) {
+            float zf[4];
+            normals4((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)b, p.key0, p.key1, zf);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (4 * b + q < jend) acc = __dadd_rn(acc, __dmul_rn((double)zf[q], __ldg(a + 4 * b + q)));
+        }
+        double R = __dadd_rn(0.0, __dmul_rn(1.0, acc));
+        R = __dadd_rn(R, p.mu[row]);
+        if (R < neg_x) atomicAdd(reinterpret_cast<unsigned int*>(p.S_acc) + (i >> 1), 1u << (16 * (unsigned)(i & 1)));
+    }
+}
+
+cudaError_t launch_exact_pairs(const PairParams& p, int num_sms, cudaStream_t s) {
+    exact_pairs_kernel<<<num_sms * 8, 128, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -119,6 +321,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams p) {
             const uint32_t f = *p.flag_count;
             flagged = f < p.flag_cap ? f : p.flag_cap;
             if (f > p.flag_cap) status = 1;  // fix-up list overflow: result incomplete
+        }
+        if (p.pair_count) {
+            const uint32_t f = *p.pair_count;
+            flagged += f < p.pair_cap ? f : p.pair_cap;
+            if (f > p.pair_cap) status = 1;
         }
         if (p.accum) { c += p.accum[0]; s += p.accum[1]; }
         p.out[0] += p.M;

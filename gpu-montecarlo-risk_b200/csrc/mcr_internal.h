@@ -72,12 +72,29 @@ struct ExactParams {
 };
 cudaError_t launch_exact(const ExactParams& p, int num_sms, cudaStream_t s);
 
+// fp64 re-evaluation of single (trial, row) decisions the slab kernel left out of S_acc (mcr_exact.cu)
+struct PairParams {
+    const unsigned long long* pair_list;   // trial << 16 | row
+    const uint32_t* pair_count;
+    uint32_t pair_cap;
+    uint64_t path_offset;
+    uint32_t key0, key1;
+    int32_t N, lower;
+    double x;
+    const double* mu;
+    const double* A_rm;                    // N x N row-major fp64
+    uint16_t* S_acc;                       // hit added here (two trials per 32-bit word)
+};
+cudaError_t launch_exact_pairs(const PairParams& p, int num_sms, cudaStream_t s);
+
 struct FinalizeParams {
     const uint64_t* block_partials;  // [n_blocks][2]
     int n_blocks;
     const unsigned long long* accum; // fix-up accumulators [2]
     const uint32_t* flag_count;
     uint32_t flag_cap;
+    const uint32_t* pair_count;      // slab path: per-decision fix-ups (counted as rechecked), or nullptr
+    uint32_t pair_cap;
     uint64_t M;
     uint64_t* out;                   // MCR_PARTIAL_WORDS, accumulated (+=)
 };
@@ -122,6 +139,10 @@ struct SlabLaunch {
     const void* d_slab_image;    // device image of this slab (slab_build)
     uint16_t* S_acc;             // [M] running per-trial hit count, bit 15 = flagged
     int32_t first_slab;
+    int32_t row_base;            // first transform row of this slab
+    unsigned long long* pair_list;  // (trial << 16 | row): single near-threshold decisions, or nullptr (whole trials get flagged)
+    uint32_t* pair_count;
+    uint32_t pair_cap;
 };
 int slab_rows();
 int slab_count(int N);

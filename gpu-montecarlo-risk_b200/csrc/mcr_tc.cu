@@ -479,9 +479,14 @@ struct TcSlabParams {
     int32_t ncols;        // normal columns this slab multiplies; the constant 1 sits in column ncols
     int32_t kb_count;     // K-blocks = ceil((ncols + 1) / 64)
     float delta_rel, delta_abs;   // scaled guard band = delta_rel * ||z||_2 + delta_abs (Cauchy-Schwarz bound on sum |a||z|)
+    float thr_max;                // upper bound of that band over all trials: every |z_j| < 7 (Box-Muller on 32-bit uniforms)
     const uint4* B_slab;  // global: kb_count x [hi 32 KB | lo 32 KB], SLAB_ROWS rows x 128 B, pre-swizzled
     uint16_t* S_acc;      // [M] running hit count, bit 15 = flagged
     int32_t first_slab;   // overwrite S_acc instead of accumulating
+    int32_t row_base;     // first transform row of this slab
+    unsigned long long* pair_list;   // (trial << 16 | row) of single near-threshold decisions, fixed up per pair
+    uint32_t* pair_count;
+    uint32_t pair_cap;
 };
 
 constexpr int SLAB_ROWS = 256;                            // transform rows per slab = UMMA N = TMEM columns of one accumulator region
@@ -491,6 +496,7 @@ constexpr uint32_t SLAB_SLOT_BYTES = SLAB_Z_BYTES + SLAB_B_BYTES;
 constexpr int SLAB_KSPLIT = 4;                             // generator threads per trial row (each owns 16 of a K-block's 64 columns)
 constexpr int SLAB_GEN_THREADS = 128 * SLAB_KSPLIT;
 constexpr int SLAB_THREADS = SLAB_GEN_THREADS + 32;
+constexpr uint32_t SLAB_KEY_MASK = 0xFFFFFC00u;            // epilogue keys: bits 10.. = |accumulator| << 1 (truncated)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
@@ -505,8 +511,8 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) tc_slab_kernel(const TcSlabPa
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t s_empty[2], s_done[2];
     __shared__ uint32_t s_tmem;
-    __shared__ uint32_t s_part_S[2][SLAB_KSPLIT][128];
-    __shared__ float s_part_band[2][SLAB_KSPLIT][128], s_part_zmax[2][SLAB_KSPLIT][128];
+    __shared__ uint32_t s_part_S[2][SLAB_KSPLIT][128], s_part_k1[2][SLAB_KSPLIT][128], s_part_k2[2][SLAB_KSPLIT][128];
+    __shared__ float s_part_zmax[2][SLAB_KSPLIT][128];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr uint32_t TMEM_COLS = 2 * SLAB_ROWS;   // two accumulator regions of SLAB_ROWS columns: all of TMEM
     constexpr int MMA_WARP = SLAB_GEN_THREADS / 32;
@@ -565,32 +571,63 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) tc_slab_kernel(const TcSlabPa
             mbar_wait(&s_done[r], (done_phase >> r) & 1u);
             done_phase ^= 1u << r;
             tc_fence_after();
-            uint32_t S = 0;
-            float band = 3.0e38f;
+            // Per accumulator a sortable key: |v| (14 mantissa bits) in the high bits, the column in bits 1..8, the sign
+            // in bit 0 (rotate left by one, then overwrite the low mantissa bits).  The two smallest keys of the
+            // trial's row tell whether none, exactly one (which one, and how the fast path decided it) or several
+            // of its decisions are inside the guard band.
+            uint32_t S = 0, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
 #pragma unroll
             for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + r * SLAB_ROWS + c0, v);
                 tmem_ld_wait();
+                float m = 3.0e38f;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                     S += v[c] >> 31;
-                    band = fminf(band, fabsf(__uint_as_float(v[c])));
+                    m = fminf(m, fabsf(__uint_as_float(v[c])));
+                }
+                // keys only where something can be inside the band (thr_max bounds every trial's band from above)
+                if (m < p.thr_max) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const uint32_t key = (__funnelshift_l(v[c], v[c], 1) & (SLAB_KEY_MASK | 1u)) | ((uint32_t)(c0 + c) << 1);
+                        k2 = min(k2, max(k1, key));
+                        k1 = min(k1, key);
+                    }
                 }
             }
             tc_fence_before();
+            const uint32_t part_cols = (uint32_t)(part * EPI_COLS) << 1;
             s_part_S[r][part][row] = S;
-            s_part_band[r][part][row] = band;
+            s_part_k1[r][part][row] = k1 == 0xFFFFFFFFu ? k1 : k1 + part_cols;   // column bits: local column + first column of this quarter (no carry: < 256)
+            s_part_k2[r][part][row] = k2 == 0xFFFFFFFFu ? k2 : k2 + part_cols;
             s_part_zmax[r][part][row] = zmax;
             named_bar_sync(3, SLAB_GEN_THREADS);   // the four column quarters of every row are in
             if (part == 0 && i < p.M) {
+                uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;
+                S = 0; zmax = 0.0f;
 #pragma unroll
-                for (int q = 1; q < SLAB_KSPLIT; ++q) {
+                for (int q = 0; q < SLAB_KSPLIT; ++q) {
                     S += s_part_S[r][q][row];
-                    band = fminf(band, s_part_band[r][q][row]);
                     zmax += s_part_zmax[r][q][row];   // total sum of squares of the trial's normals in this slab
+                    const uint32_t a = s_part_k1[r][q][row], b = s_part_k2[r][q][row];
+                    m2 = min(m2, max(m1, a)); m1 = min(m1, a);
+                    m2 = min(m2, max(m1, b)); m1 = min(m1, b);
                 }
-                const uint32_t flagged = band < __fmaf_rn(p.delta_rel, sqrtf(zmax) * 1.0001f, p.delta_abs) ? 0x8000u : 0u;
+                const float thr = __fmaf_rn(p.delta_rel, sqrtf(zmax) * 1.0001f, p.delta_abs);
+                const uint32_t thr_key = __float_as_uint(thr) << 1;
+                uint32_t flagged = 0u;
+                if ((m1 & SLAB_KEY_MASK) < thr_key) {
+                    if ((m2 & SLAB_KEY_MASK) < thr_key || !p.pair_list) {
+                        flagged = 0x8000u;           // several near-threshold decisions: the whole trial goes to the fp64 kernel
+                    } else {
+                        S -= m1 & 1u;                // leave the one uncertain decision out; exact_pairs_kernel adds the fp64 one
+                        const uint32_t slot = atomicAdd(p.pair_count, 1u);
+                        if (slot < p.pair_cap)
+                            p.pair_list[slot] = ((unsigned long long)i << 16) | (unsigned long long)(p.row_base + ((m1 >> 1) & 0xFFu));
+                    }
+                }
                 const uint32_t old = p.first_slab ? 0u : (uint32_t)p.S_acc[i];
                 p.S_acc[i] = (uint16_t)(((old & 0x7FFFu) + S) | (old & 0x8000u) | flagged);
             }
@@ -887,7 +924,9 @@ cudaError_t slab_launch(const SlabLaunch& l, int num_sms, cudaStream_t s) {
     p.M = l.M; p.path_offset = l.path_offset; p.key0 = l.key0; p.key1 = l.key1;
     p.ncols = l.ncols; p.kb_count = slab_kblocks(l.ncols);
     p.delta_rel = (float)(l.delta_rel * TC_SCALE); p.delta_abs = (float)(l.delta_abs * TC_SCALE);
+    p.thr_max = p.delta_rel * 7.0f * sqrtf((float)l.ncols) * 1.001f + p.delta_abs;
     p.B_slab = reinterpret_cast<const uint4*>(l.d_slab_image); p.S_acc = l.S_acc; p.first_slab = l.first_slab;
+    p.row_base = l.row_base; p.pair_list = l.pair_list; p.pair_count = l.pair_count; p.pair_cap = l.pair_cap;
     const uint64_t tiles = (l.M + tc::TILE_M - 1) / tc::TILE_M;
     const int grid = (int)std::min<uint64_t>((uint64_t)num_sms, tiles ? tiles : 1);
     tc_slab_kernel<<<grid, SLAB_THREADS, smem, s>>>(p);
