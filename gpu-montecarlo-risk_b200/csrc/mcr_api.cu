@@ -152,6 +152,8 @@ int mcr_create(int device, mcr_engine** out) {
     for (int i = 0; i < 2 * MAX_TIMED_CHUNKS; ++i) ok(cudaEventCreate(&e->evk[i]));
     ok(cudaMalloc(&e->d_flag_list, sizeof(uint32_t) * FLAG_CAP));
     ok(cudaMalloc(&e->d_flag_count, sizeof(uint32_t)));
+    ok(cudaMalloc(&e->d_pair_list, sizeof(unsigned long long) * PAIR_CAP));
+    ok(cudaMalloc(&e->d_pair_count, sizeof(uint32_t)));
     ok(cudaMalloc(&e->d_accum, sizeof(unsigned long long) * 2));
     ok(cudaMalloc(&e->d_block_partials, sizeof(uint64_t) * 2 * MAX_GRID));
     ok(cudaMalloc(&e->d_partials, sizeof(uint64_t) * MCR_PARTIAL_WORDS));
@@ -210,9 +212,10 @@ int mcr_upload_model(mcr_engine* e, int N, const double* mu, const double* A, in
     // fp64 copies for the exact / fix-up kernel (A column-major)
     if (N != e->N_alloc) {
         cudaFree(e->d_mu); cudaFree(e->d_Acm); cudaFree(e->d_Arm);
-        e->d_mu = nullptr; e->d_Acm = nullptr; e->d_Arm = nullptr; e->Arm_gen = 0; e->N_alloc = 0;
+        e->d_mu = nullptr; e->d_Acm = nullptr; e->d_Arm = nullptr; e->N_alloc = 0;
         MCR_CUDA(cudaMalloc(&e->d_mu, sizeof(double) * N));
         MCR_CUDA(cudaMalloc(&e->d_Acm, sizeof(double) * (size_t)N * N));
+        MCR_CUDA(cudaMalloc(&e->d_Arm, sizeof(double) * (size_t)N * N));
         e->N_alloc = N;
     }
     std::vector<double> Acm((size_t)N * N);
@@ -220,6 +223,7 @@ int mcr_upload_model(mcr_engine* e, int N, const double* mu, const double* A, in
         for (int j = 0; j < N; ++j) Acm[(size_t)j * N + i] = A[(size_t)i * N + j];
     MCR_CUDA(cudaMemcpy(e->d_mu, mu, sizeof(double) * N, cudaMemcpyHostToDevice));
     MCR_CUDA(cudaMemcpy(e->d_Acm, Acm.data(), sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice));
+    MCR_CUDA(cudaMemcpy(e->d_Arm, A, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice));   // row-major, per-decision fix-up
     // guard-band ingredient: gamma_i * sum_j |A_ij| with gamma_i = (terms_i + 3) * 2^-24
     const double u = std::ldexp(1.0, -24);
     e->gamma_rowabs_max = 0;
@@ -467,6 +471,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         tc_grid_full = std::min(e->num_sms * bps, MAX_GRID);
         tl.key0 = key0; tl.key1 = key1; tl.k = k; tl.d_image = e->d_tc_image;
         tl.flag_list = e->d_flag_list; tl.flag_count = e->d_flag_count; tl.flag_cap = FLAG_CAP;
+        tl.pair_list = plan.recheck ? e->d_pair_list : nullptr; tl.pair_count = e->d_pair_count; tl.pair_cap = PAIR_CAP;
         tl.block_partials = e->d_block_partials;
     }
 
@@ -482,14 +487,6 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             e->slab_image_cap = bytes; e->slab_gen = 0;
         }
         if (!e->d_S_acc) MCR_CUDA(cudaMalloc(&e->d_S_acc, sizeof(uint16_t) * SLAB_CHUNK_PATHS));
-        if (!e->d_pair_list) MCR_CUDA(cudaMalloc(&e->d_pair_list, sizeof(unsigned long long) * PAIR_CAP));
-        if (!e->d_pair_count) MCR_CUDA(cudaMalloc(&e->d_pair_count, sizeof(uint32_t)));
-        if (!e->d_Arm) MCR_CUDA(cudaMalloc(&e->d_Arm, sizeof(double) * (size_t)N * N));
-        if (e->Arm_gen != e->gen) {
-            MCR_CUDA(cudaStreamSynchronize(s));
-            MCR_CUDA(cudaMemcpyAsync(e->d_Arm, e->A.data(), sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, s));
-            e->Arm_gen = e->gen;
-        }
         std::vector<double> c(N);
         for (int i = 0; i < N; ++i) c[i] = e->mu[i] + x;
         if (e->slab_gen != e->gen || e->slab_x != x) {
@@ -525,7 +522,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         if (m == 0) break;
         MCR_CUDA(cudaMemsetAsync(e->d_accum, 0, sizeof(unsigned long long) * 2, s));
         MCR_CUDA(cudaMemsetAsync(e->d_flag_count, 0, sizeof(uint32_t), s));
-        if (plan.slab) MCR_CUDA(cudaMemsetAsync(e->d_pair_count, 0, sizeof(uint32_t), s));
+        MCR_CUDA(cudaMemsetAsync(e->d_pair_count, 0, sizeof(uint32_t), s));
         FinalizeParams fin{};
         fin.M = m; fin.out = d_out; fin.accum = e->d_accum;
         ExactParams xp{};
@@ -581,6 +578,14 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             if (timed) { MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed + 1], s)); ++e->n_timed; }
             ++launches;
             if (plan.recheck) {
+                PairParams pp{};   // trials with a single near-threshold decision: that row alone in fp64
+                pp.pair_list = e->d_pair_list; pp.pair_count = e->d_pair_count; pp.pair_cap = PAIR_CAP;
+                pp.path_offset = path_offset + done; pp.key0 = key0; pp.key1 = key1;
+                pp.N = N; pp.lower = e->lower ? 1 : 0; pp.x = x; pp.mu = e->d_mu; pp.A_rm = e->d_Arm;
+                pp.k = k; pp.S_out = xp.S_out; pp.accum = e->d_accum;
+                MCR_CUDA(launch_exact_pairs(pp, e->num_sms, s));
+                ++launches;
+                fin.pair_count = e->d_pair_count; fin.pair_cap = PAIR_CAP;
                 xp.flag_list = e->d_flag_list; xp.flag_count = e->d_flag_count; xp.flag_cap = FLAG_CAP;
                 MCR_CUDA(launch_exact(xp, e->num_sms, s));
                 ++launches;

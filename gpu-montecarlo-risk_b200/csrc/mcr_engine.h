@@ -55,7 +55,6 @@ struct mcr_engine {
     unsigned long long* d_pair_list = nullptr;   // single near-threshold (trial, row) decisions of a chunk
     uint32_t* d_pair_count = nullptr;
     double* d_Arm = nullptr;                     // fp64 transform, row-major (per-decision fix-up)
-    uint64_t Arm_gen = 0;
     double gamma_rowabs_max = 0;  // max_i gamma_i * sum_j |A_ij|
     // scratch
     uint32_t* d_flag_list = nullptr;

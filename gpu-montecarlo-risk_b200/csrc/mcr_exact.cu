@@ -267,7 +267,8 @@ cudaError_t launch_exact(const ExactParams& p, int num_sms, cudaStream_t s) {
 
 // ---- single decisions of the slab path ------------------------------------------------------------------------
 // One thread per (trial, row): the trial's normals are re-derived from the counter-based stream in column order
-// and the row's sum is accumulated exactly as in exact_kernel; a hit is added to the trial's uint16 in S_acc.
+// and the row's sum is accumulated exactly as in exact_kernel.  Slab path: a hit is added to the trial's uint16 in
+// S_acc (counted later); N <= 128: the entry carries the trial's other hits, so S is final and counted here.
 __global__ void __launch_bounds__(128) exact_pairs_kernel(const PairParams p) {
     const uint32_t c = *p.pair_count;
     const uint32_t n = c < p.pair_cap ? c : p.pair_cap;
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(128) exact_pairs_kernel(const PairParams p) {
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const unsigned long long e = p.pair_list[t];
         const uint64_t i = e >> 16;
-        const int row = (int)(e & 0xFFFFu);
+        const int row = p.S_acc ? (int)(e & 0xFFFFu) : (int)(e & 0xFFu);
         const uint64_t path = p.path_offset + i;
         const int jend = p.lower ? row + 1 : p.N;
         const double* a = p.A_rm + (size_t)row * p.N;
@@ -289,7 +290,15 @@ __global__ void __launch_bounds__(128) exact_pairs_kernel(const PairParams p) {
         }
         double R = __dadd_rn(0.0, __dmul_rn(1.0, acc));
         R = __dadd_rn(R, p.mu[row]);
-        if (R < neg_x) atomicAdd(reinterpret_cast<unsigned int*>(p.S_acc) + (i >> 1), 1u << (16 * (unsigned)(i & 1)));
+        const int hit = R < neg_x ? 1 : 0;
+        if (p.S_acc) {
+            if (hit) atomicAdd(reinterpret_cast<unsigned int*>(p.S_acc) + (i >> 1), 1u << (16 * (unsigned)(i & 1)));
+        } else {
+            const int S = (int)((e >> 8) & 0xFFu) + hit;
+            if (S >= p.k) atomicAdd(&p.accum[0], 1ull);
+            atomicAdd(&p.accum[1], (unsigned long long)S);
+            if (p.S_out) p.S_out[i] = S;
+        }
     }
 }
 

@@ -74,7 +74,7 @@ cudaError_t launch_exact(const ExactParams& p, int num_sms, cudaStream_t s);
 
 // fp64 re-evaluation of single (trial, row) decisions the slab kernel left out of S_acc (mcr_exact.cu)
 struct PairParams {
-    const unsigned long long* pair_list;   // trial << 16 | row
+    const unsigned long long* pair_list;   // slab path: trial << 16 | row;  N <= 128: trial << 16 | S_rest << 8 | row
     const uint32_t* pair_count;
     uint32_t pair_cap;
     uint64_t path_offset;
@@ -83,7 +83,10 @@ struct PairParams {
     double x;
     const double* mu;
     const double* A_rm;                    // N x N row-major fp64
-    uint16_t* S_acc;                       // hit added here (two trials per 32-bit word)
+    uint16_t* S_acc;                       // slab path: hit added here (two trials per 32-bit word); else nullptr and:
+    int32_t k;                             // S = S_rest + hit is final: counted into accum like exact_kernel does
+    int32_t* S_out;
+    unsigned long long* accum;
 };
 cudaError_t launch_exact_pairs(const PairParams& p, int num_sms, cudaStream_t s);
 
@@ -111,6 +114,9 @@ struct TcLaunch {
     uint32_t* flag_list;
     uint32_t* flag_count;
     uint32_t flag_cap;
+    unsigned long long* pair_list;  // trial << 16 | S without that decision << 8 | row: single near-threshold decisions (or nullptr)
+    uint32_t* pair_count;
+    uint32_t pair_cap;
     uint64_t* block_partials;
     // portfolio extension
     int32_t portfolio;

@@ -139,6 +139,9 @@ struct TcParams {
     uint32_t* flag_list;
     uint32_t* flag_count;
     uint32_t flag_cap;
+    unsigned long long* pair_list;   // single near-threshold decisions (trial << 16 | S_rest << 8 | row), or nullptr
+    uint32_t* pair_count;
+    uint32_t pair_cap;
     uint64_t* block_partials;
     // portfolio extension (north-star A7; no reference code): accumulator column NOUT-1 holds w.R
     int32_t portfolio;            // 0 = off (column NOUT-1 is an ordinary padded / asset row)
@@ -293,13 +296,28 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
         // epilogue of a finished tile: TMEM -> registers, threshold + guard band
         auto epilogue = [&](uint64_t i, float zmax) {
             tc_fence_after();
-            uint32_t S = 0;
+            // Near-threshold decisions are rare.  The scan below counts how many of the trial's decisions are inside
+            // its guard band and remembers the last one (column, fast-path decision); it runs only where the smallest
+            // |accumulator| is under the band: per 32-column group (wide tiles), or after the fast pass on a second
+            // read of the accumulators when any lane of the warp needs it (narrow tiles, where that is cheaper).
+            constexpr bool SCAN_INLINE = NOUT > 64;
+            const float thr = __fmaf_rn(p.delta_rel, zmax, p.delta_abs);
+            uint32_t S = 0, n_amb = 0, amb = 0;
             float band = 3.0e38f;
+            auto scan = [&](const uint32_t (&v)[32], int c0) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if (c0 + c < NOUT - 1 || (c0 + c == NOUT - 1 && !p.portfolio)) {
+                        if (fabsf(__uint_as_float(v[c])) < thr) { ++n_amb; amb = ((uint32_t)(c0 + c) << 1) | (v[c] >> 31); }
+                    }
+                }
+            };
 #pragma unroll
             for (int c0 = 0; c0 < (MCR_TC_ABLATE == 2 ? 0 : NOUT); c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
                 tmem_ld_wait();
+                if (SCAN_INLINE) band = 3.0e38f;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                     if (c0 + c < NOUT - 1) {
@@ -325,9 +343,24 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
                         }
                     }
                 }
+                if (SCAN_INLINE && band < thr) scan(v, c0);
+            }
+            if (!SCAN_INLINE && __any_sync(0xffffffffu, band < thr)) {   // a few warps in a hundred: read the accumulators again
+#pragma unroll 1
+                for (int c0 = 0; c0 < NOUT; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                    scan(v, c0);
+                }
             }
             if (i < p.M) {
-                if (band < __fmaf_rn(p.delta_rel, zmax, p.delta_abs)) {
+                if (n_amb == 1 && p.pair_list) {
+                    // one uncertain decision: exact_pairs_kernel re-evaluates that row in fp64 and counts the trial
+                    const uint32_t slot = atomicAdd(p.pair_count, 1u);
+                    if (slot < p.pair_cap)
+                        p.pair_list[slot] = ((unsigned long long)i << 16) | (unsigned long long)(((S - (amb & 1u)) << 8) | (amb >> 1));
+                } else if (n_amb != 0) {
                     const uint32_t slot = atomicAdd(p.flag_count, 1u);
                     if (slot < p.flag_cap) p.flag_list[slot] = (uint32_t)i;
                 } else {
@@ -863,6 +896,7 @@ cudaError_t tc_launch(int N, int rows, const TcLaunch& l, int grid, cudaStream_t
     p.delta_rel = (float)(l.delta_rel * TC_SCALE); p.delta_abs = (float)(l.delta_abs * TC_SCALE);  // accumulators are scaled
     p.B_image = reinterpret_cast<const uint4*>(l.d_image); p.S_out = l.S_out;
     p.flag_list = l.flag_list; p.flag_count = l.flag_count; p.flag_cap = l.flag_cap; p.block_partials = l.block_partials;
+    p.pair_list = l.pair_list; p.pair_count = l.pair_count; p.pair_cap = l.pair_cap;
     p.portfolio = l.portfolio; p.port_thresh = (float)(-l.port_x * TC_SCALE);
     p.hist_lo = (float)l.hist_lo; p.hist_inv_w = (float)(1.0 / l.hist_width);
     p.port_acc = l.port_acc; p.port_hist = l.port_hist; p.port_hist_sum = l.port_hist_sum;

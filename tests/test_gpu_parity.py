@@ -313,7 +313,7 @@ def test_tensor_kernels_ragged_trial_counts_and_offsets(engine, oracle, N):
 @pytest.mark.parametrize("N,mode,M", [(160, api.TRANSFORM_LOWER, 20000), (200, api.TRANSFORM_GSL_FULL, 8000),
                                       (600, api.TRANSFORM_LOWER, 5000), (1024, api.TRANSFORM_LOWER, 1500)])
 def test_large_n_row_slab_tensor_kernel_bit_exact(engine, oracle, N, mode, M):
-    """N > 128 (Stoxx600 shape): tensor-core kernel over row slabs of 128 assets; still bit-exact."""
+    """N > 128 (Stoxx600 shape): tensor-core kernel over row slabs of 256 assets; still bit-exact."""
     m = synthetic_model(N)
     A = engine.upload_sigma(m.mu, m.Sigma, mode)
     Z, _ = engine.dump_normals(M, 11, path_offset=77)
@@ -329,6 +329,30 @@ def test_large_n_row_slab_tensor_kernel_bit_exact(engine, oracle, N, mode, M):
     np.testing.assert_array_equal(h.S_values, r0["S_values"])
     with pytest.raises(api.McrError, match="no FFMA instantiation"):
         engine.run(1000, 11, m.x, m.k, kernel=api.KERNEL_FFMA)
+
+
+def test_slab_fixup_paths_under_a_wide_band():
+    """The tensor kernels have two fix-ups: a single near-threshold decision is re-evaluated alone (exact_pairs_kernel), a
+    trial with several goes to the full fp64 kernel.  A band widened 32x (env knob, read once per process) makes both
+    common -- and trials hitting both in different slabs -- and the totals must still equal the fp64 kernel's."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from mcr_b200 import api\n"
+        "from mcr_b200.synthetic import synthetic_model\n"
+        "e = api.Engine(0)\n"
+        "for N, M in ((50, 400000), (128, 200000), (160, 40000), (600, 20000), (1000, 6000)):\n"
+        "    m = synthetic_model(N); e.upload_sigma(m.mu, m.Sigma)\n"
+        "    r = e.run(M, 21, m.x, m.k, path_offset=3); x = e.run(M, 21, m.x, m.k, path_offset=3, kernel=api.KERNEL_EXACT)\n"
+        "    assert r.kernel == 'tensor' and x.kernel == 'exact'\n"
+        "    assert (r.count, r.sum_S) == (x.count, x.sum_S), (N, r.count, x.count, r.sum_S, x.sum_S)\n"
+        "    print(N, r.n_rechecked)\n"
+    ) % str(Path(__file__).resolve().parent.parent / "gpu-montecarlo-risk_b200")
+    import os, subprocess, sys
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MCR_TC_BAND_SCALE="32"), capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    rechecked = {int(l.split()[0]): int(l.split()[1]) for l in p.stdout.strip().splitlines()}
+    assert rechecked[50] > 2000 and rechecked[128] > 5000, rechecked   # the wide band was in force
+    assert rechecked[160] > 400 and rechecked[600] > 2000 and rechecked[1000] > 1000, rechecked
 
 
 def test_error_behaviour():
