@@ -324,7 +324,7 @@ def main():
                  else f"ffma_path_kernel<NT={one.padded_N},LOWER,philox>")
         roof = {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf if peak_tf else None,
-                "traffic": 45568 if one.kernel == "tensor" else 71168,  # dram__bytes_read+write per launch, ncu --set full (profiles/r01_bench_tc_n50_ncu_summary.txt)
+                "traffic": 64512 if one.kernel == "tensor" else 71168,  # dram__bytes_read+write per launch, ncu --set full (profiles/r01_bench_tc_n50_ncu_summary.txt)
                 "kernel": kname, "kernel_ms_per_launch": k_ms,
                 "launches_timed_per_step": launches_per_kernel_step,
                 "flops_per_sim": flops_per_sim(N),
