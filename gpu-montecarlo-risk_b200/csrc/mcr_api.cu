@@ -175,7 +175,7 @@ int mcr_destroy(mcr_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_mu); cudaFree(e->d_Acm); cudaFree(e->d_tc_image); cudaFree(e->d_slab_image); cudaFree(e->d_S_acc);
-    cudaFree(e->d_pair_list); cudaFree(e->d_pair_count); cudaFree(e->d_Arm);
+    cudaFree(e->d_pair_list); cudaFree(e->d_pair_count); cudaFree(e->d_Arm); cudaFree(e->d_wide_image); cudaFree(e->d_wide_c);
     cudaFree(e->d_flag_list); cudaFree(e->d_flag_count); cudaFree(e->d_accum);
     cudaFree(e->d_block_partials); cudaFree(e->d_partials);
     cudaFree(e->d_port_acc); cudaFree(e->d_port_hist); cudaFree(e->d_port_hist_sum);
@@ -260,7 +260,8 @@ struct RunPlan {
     int NT;
     bool recheck;
     bool portfolio;   // accumulator row N carries the portfolio return (tensor kernel only)
-    bool slab;        // N > 128: tensor kernel over row slabs of 128 assets
+    bool slab;        // N > 128: tensor kernel over row slabs of 256 assets (MCR_LARGE_N=slab)
+    bool wide;        // N > 128: single-pass tensor kernel, all accumulators in TMEM (default)
     int rows;         // accumulator rows needed: N (+1 with the portfolio row)
 };
 
@@ -281,7 +282,13 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
     plan->slab = false;
     plan->rows = e->N + (plan->portfolio ? 1 : 0);
     if (!normals && !plan->portfolio && e->N > tc_max_n() && (want == MCR_KERNEL_AUTO || want == MCR_KERNEL_TENSOR)) {
-        plan->kernel = MCR_KERNEL_TENSOR; plan->slab = true; plan->NT = slab_rows() * slab_count(e->N);
+        // two kernels for N > 128 (profiles/r01_large_n_sweep.log): the single-pass kernel wins where 3..5 slabs of 128 rows
+        // fill TMEM with tiles of 96-128 trials (257 <= N <= 640); elsewhere the row-slab kernel does.  MCR_LARGE_N=slab|wide forces one.
+        static const int forced = [] { const char* v = getenv("MCR_LARGE_N"); return !v ? 0 : !strcmp(v, "slab") ? 1 : !strcmp(v, "wide") ? 2 : 0; }();
+        plan->kernel = MCR_KERNEL_TENSOR;
+        const bool wide_wins = wide_slabs(e->N) >= 3 && wide_slabs(e->N) <= 5;
+        if (wide_supported(e->N) && (forced == 2 || (forced == 0 && wide_wins))) { plan->wide = true; plan->NT = 128 * wide_slabs(e->N); }
+        else { plan->slab = true; plan->NT = slab_rows() * slab_count(e->N); }
         return 0;
     }
     const bool tc_ok = !normals && tc_supported(plan->rows);
@@ -405,7 +412,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
 
     TcLaunch tl{};
     int tc_grid_full = 0;
-    if (plan.kernel == MCR_KERNEL_TENSOR && !plan.slab) {
+    if (plan.kernel == MCR_KERNEL_TENSOR && !plan.slab && !plan.wide) {
         // split, swizzled transform image (depends on x through the constant column): rebuilt only when
         // the model or x changed
         const int rows = plan.rows;
@@ -476,7 +483,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
     }
 
     // ---- row-slab tensor path (N > 128): per-slab images, per-trial uint16 accumulator ----
-    const uint64_t chunk_paths = plan.slab ? SLAB_CHUNK_PATHS : CHUNK_PATHS;
+    const uint64_t chunk_paths = (plan.slab || plan.wide) ? SLAB_CHUNK_PATHS : CHUNK_PATHS;
     std::vector<double> slab_drel, slab_dabs;
     if (plan.slab) {
         const int ns = slab_count(N);
@@ -517,6 +524,51 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         }
     }
 
+    // ---- single-pass wide tensor path (128 < N <= 1024): block image, thresholds, per-slab guard bands ----
+    WideLaunch wl{};
+    if (plan.wide) {
+        const int ns = wide_slabs(N), kbn = wide_kblocks(N);
+        const size_t bytes = wide_image_bytes(N, e->lower);
+        if (e->wide_image_cap < bytes) {
+            cudaFree(e->d_wide_image); cudaFree(e->d_wide_c); e->d_wide_image = nullptr; e->d_wide_c = nullptr; e->wide_image_cap = 0;
+            MCR_CUDA(cudaMalloc(&e->d_wide_image, bytes));
+            MCR_CUDA(cudaMalloc(&e->d_wide_c, sizeof(float) * 128 * WIDE_MAX_SLABS));
+            e->wide_image_cap = bytes; e->wide_gen = 0;
+        }
+        std::vector<double> c(N);
+        for (int i = 0; i < N; ++i) c[i] = e->mu[i] + x;
+        if (e->wide_gen != e->gen || e->wide_x != x) {
+            e->wide_host_image.resize(bytes);
+            e->wide_host_c.assign(128 * WIDE_MAX_SLABS, 0.f);
+            wide_build(N, e->lower, e->A.data(), c.data(), e->wide_host_image.data(), e->wide_host_c.data());
+            MCR_CUDA(cudaStreamSynchronize(s));   // a previous run may still read the old image
+            MCR_CUDA(cudaMemcpyAsync(e->d_wide_image, e->wide_host_image.data(), bytes, cudaMemcpyHostToDevice, s));
+            MCR_CUDA(cudaMemcpyAsync(e->d_wide_c, e->wide_host_c.data(), sizeof(float) * 128 * ns, cudaMemcpyHostToDevice, s));
+            e->wide_gen = e->gen; e->wide_x = x;
+        }
+        // guard band per 128-row slab, same budget as the row-slab kernel: fp16x3 split (3 * 2^-22) + fp32 accumulation over
+        // 12 MMAs per K-block, relative to ||a_i||_2 ||z||_2 (Cauchy-Schwarz; the kernel uses the norm of all N normals)
+        static const double band_scale = [] { const char* v = getenv("MCR_TC_BAND_SCALE"); return v && *v ? atof(v) : 1.0; }();
+        for (int t = 0; t < ns; ++t) {
+            const int kbt = e->lower ? std::min(2 * t + 2, kbn) : kbn;
+            const double gamma = std::ldexp(1.0, -19) * std::max(1.0, kbt / 8.0);
+            double rownorm = 0, cabs = 1e-300;
+            for (int i = 128 * t; i < std::min(N, 128 * (t + 1)); ++i) {
+                double ss = 0;
+                for (int j = 0; j < N; ++j) ss += e->A[(size_t)i * N + j] * e->A[(size_t)i * N + j];
+                rownorm = std::max(rownorm, std::sqrt(ss));
+                cabs = std::max(cabs, std::fabs(c[i]));
+            }
+            wl.delta_rel[t] = plan.recheck ? band_scale * 2.0 * gamma * rownorm : 0.0;
+            wl.delta_abs[t] = plan.recheck ? band_scale * 2.0 * gamma * cabs + 1e-30 : 0.0;
+        }
+        wl.key0 = key0; wl.key1 = key1; wl.N = N; wl.k = k; wl.lower = e->lower ? 1 : 0;
+        wl.d_image = e->d_wide_image; wl.d_c_scaled = e->d_wide_c;
+        wl.flag_list = e->d_flag_list; wl.flag_count = e->d_flag_count; wl.flag_cap = FLAG_CAP;
+        wl.pair_list = plan.recheck ? e->d_pair_list : nullptr; wl.pair_count = e->d_pair_count; wl.pair_cap = PAIR_CAP;
+        wl.block_partials = e->d_block_partials;
+    }
+
     for (uint64_t done = 0; done < M || (M == 0 && done == 0); done += chunk_paths) {
         const uint64_t m = std::min<uint64_t>(chunk_paths, M - done);
         if (m == 0) break;
@@ -553,7 +605,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
                 PairParams pp{};
                 pp.pair_list = e->d_pair_list; pp.pair_count = e->d_pair_count; pp.pair_cap = PAIR_CAP;
                 pp.path_offset = path_offset + done; pp.key0 = key0; pp.key1 = key1;
-                pp.N = N; pp.lower = e->lower ? 1 : 0; pp.x = x; pp.mu = e->d_mu; pp.A_rm = e->d_Arm; pp.S_acc = e->d_S_acc;
+                pp.N = N; pp.lower = e->lower ? 1 : 0; pp.x = x; pp.mu = e->d_mu; pp.A_rm = e->d_Arm; pp.S_acc = e->d_S_acc; pp.mode = 0;
                 MCR_CUDA(launch_exact_pairs(pp, e->num_sms, s));
                 ++launches;
             }
@@ -568,6 +620,28 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             fin.block_partials = e->d_block_partials; fin.n_blocks = grid;
             fin.flag_count = e->d_flag_count; fin.flag_cap = FLAG_CAP;
             if (plan.recheck) { fin.pair_count = e->d_pair_count; fin.pair_cap = PAIR_CAP; }
+        } else if (plan.wide) {
+            wl.M = m; wl.path_offset = path_offset + done; wl.S_out = xp.S_out;
+            const bool timed = e->n_timed < MAX_TIMED_CHUNKS;
+            if (timed) MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed], s));
+            MCR_CUDA(wide_launch(wl, e->num_sms, s));
+            if (timed) { MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed + 1], s)); ++e->n_timed; }
+            ++launches;
+            if (plan.recheck) {
+                PairParams pp{};
+                pp.pair_list = e->d_pair_list; pp.pair_count = e->d_pair_count; pp.pair_cap = PAIR_CAP;
+                pp.path_offset = path_offset + done; pp.key0 = key0; pp.key1 = key1;
+                pp.N = N; pp.lower = e->lower ? 1 : 0; pp.x = x; pp.mu = e->d_mu; pp.A_rm = e->d_Arm;
+                pp.k = k; pp.S_out = xp.S_out; pp.accum = e->d_accum; pp.mode = 2;
+                MCR_CUDA(launch_exact_pairs(pp, e->num_sms, s));
+                ++launches;
+                fin.pair_count = e->d_pair_count; fin.pair_cap = PAIR_CAP;
+                xp.flag_list = e->d_flag_list; xp.flag_count = e->d_flag_count; xp.flag_cap = FLAG_CAP;
+                MCR_CUDA(launch_exact(xp, e->num_sms, s));
+                ++launches;
+            }
+            fin.block_partials = e->d_block_partials; fin.n_blocks = wide_grid(m, N, e->num_sms);
+            fin.flag_count = e->d_flag_count; fin.flag_cap = FLAG_CAP;
         } else if (plan.kernel == MCR_KERNEL_TENSOR) {
             tl.M = m; tl.path_offset = path_offset + done; tl.S_out = xp.S_out;
             const uint64_t tiles = (m + 127) / 128;
@@ -582,7 +656,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
                 pp.pair_list = e->d_pair_list; pp.pair_count = e->d_pair_count; pp.pair_cap = PAIR_CAP;
                 pp.path_offset = path_offset + done; pp.key0 = key0; pp.key1 = key1;
                 pp.N = N; pp.lower = e->lower ? 1 : 0; pp.x = x; pp.mu = e->d_mu; pp.A_rm = e->d_Arm;
-                pp.k = k; pp.S_out = xp.S_out; pp.accum = e->d_accum;
+                pp.k = k; pp.S_out = xp.S_out; pp.accum = e->d_accum; pp.mode = 1;
                 MCR_CUDA(launch_exact_pairs(pp, e->num_sms, s));
                 ++launches;
                 fin.pair_count = e->d_pair_count; fin.pair_cap = PAIR_CAP;

@@ -52,6 +52,14 @@ struct mcr_engine {
     std::vector<uint8_t> slab_host_image;
     std::vector<size_t> slab_offsets;
     uint16_t* d_S_acc = nullptr;
+    // single-pass wide tensor path (128 < N <= 1024)
+    void* d_wide_image = nullptr;
+    float* d_wide_c = nullptr;
+    size_t wide_image_cap = 0;
+    uint64_t wide_gen = 0;
+    double wide_x = 0;
+    std::vector<uint8_t> wide_host_image;
+    std::vector<float> wide_host_c;
     unsigned long long* d_pair_list = nullptr;   // single near-threshold (trial, row) decisions of a chunk
     uint32_t* d_pair_count = nullptr;
     double* d_Arm = nullptr;                     // fp64 transform, row-major (per-decision fix-up)

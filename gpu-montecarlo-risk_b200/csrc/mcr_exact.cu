@@ -275,8 +275,9 @@ __global__ void __launch_bounds__(128) exact_pairs_kernel(const PairParams p) {
     const double neg_x = -p.x;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const unsigned long long e = p.pair_list[t];
-        const uint64_t i = e >> 16;
-        const int row = p.S_acc ? (int)(e & 0xFFFFu) : (int)(e & 0xFFu);
+        const uint64_t i = p.mode == 2 ? e >> 21 : e >> 16;
+        const int row = p.mode == 0 ? (int)(e & 0xFFFFu) : p.mode == 1 ? (int)(e & 0xFFu) : (int)(e & 0x3FFu);
+        const int S_rest = p.mode == 1 ? (int)((e >> 8) & 0xFFu) : (int)((e >> 10) & 0x7FFu);
         const uint64_t path = p.path_offset + i;
         const int jend = p.lower ? row + 1 : p.N;
         const double* a = p.A_rm + (size_t)row * p.N;
@@ -291,10 +292,10 @@ __global__ void __launch_bounds__(128) exact_pairs_kernel(const PairParams p) {
         double R = __dadd_rn(0.0, __dmul_rn(1.0, acc));
         R = __dadd_rn(R, p.mu[row]);
         const int hit = R < neg_x ? 1 : 0;
-        if (p.S_acc) {
+        if (p.mode == 0) {
             if (hit) atomicAdd(reinterpret_cast<unsigned int*>(p.S_acc) + (i >> 1), 1u << (16 * (unsigned)(i & 1)));
         } else {
-            const int S = (int)((e >> 8) & 0xFFu) + hit;
+            const int S = S_rest + hit;
             if (S >= p.k) atomicAdd(&p.accum[0], 1ull);
             atomicAdd(&p.accum[1], (unsigned long long)S);
             if (p.S_out) p.S_out[i] = S;

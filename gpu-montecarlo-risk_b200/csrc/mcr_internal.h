@@ -74,7 +74,9 @@ cudaError_t launch_exact(const ExactParams& p, int num_sms, cudaStream_t s);
 
 // fp64 re-evaluation of single (trial, row) decisions the slab kernel left out of S_acc (mcr_exact.cu)
 struct PairParams {
-    const unsigned long long* pair_list;   // slab path: trial << 16 | row;  N <= 128: trial << 16 | S_rest << 8 | row
+    const unsigned long long* pair_list;   // mode 0 (slab path): trial << 16 | row;  1 (N <= 128): trial << 16 | S_rest << 8 | row;
+                                           // 2 (single-pass wide kernel): trial << 21 | S_rest << 10 | row
+    int32_t mode;
     const uint32_t* pair_count;
     uint32_t pair_cap;
     uint64_t path_offset;
@@ -83,8 +85,8 @@ struct PairParams {
     double x;
     const double* mu;
     const double* A_rm;                    // N x N row-major fp64
-    uint16_t* S_acc;                       // slab path: hit added here (two trials per 32-bit word); else nullptr and:
-    int32_t k;                             // S = S_rest + hit is final: counted into accum like exact_kernel does
+    uint16_t* S_acc;                       // mode 0: hit added here (two trials per 32-bit word)
+    int32_t k;                             // modes 1, 2: S = S_rest + hit is final: counted into accum like exact_kernel does
     int32_t* S_out;
     unsigned long long* accum;
 };
@@ -158,6 +160,33 @@ void slab_build(int N, bool lower, const double* A, const double* c, uint8_t* im
 cudaError_t slab_launch(const SlabLaunch& l, int num_sms, cudaStream_t s);
 cudaError_t slab_count_launch(uint64_t M, const uint16_t* S_acc, int k, int32_t* S_out, uint32_t* flag_list,
                               uint32_t* flag_count, uint32_t flag_cap, uint64_t* block_partials, int grid, cudaStream_t s);
+
+// ---- single-pass tensor-core path for 128 < N <= 1024 (mcr_wide.cu) --------------------------------------
+constexpr int WIDE_MAX_SLABS = 8;
+struct WideLaunch {
+    uint64_t M, path_offset;
+    uint32_t key0, key1;
+    int32_t N, k, lower;
+    const void* d_image;         // wide_build image on the device
+    const float* d_c_scaled;     // wide_build thresholds on the device
+    double delta_rel[WIDE_MAX_SLABS], delta_abs[WIDE_MAX_SLABS];   // unscaled guard band per 128-row slab (relative to ||z||_2)
+    int32_t* S_out;
+    uint32_t* flag_list;
+    uint32_t* flag_count;
+    uint32_t flag_cap;
+    unsigned long long* pair_list;   // trial << 21 | other hits << 10 | row, or nullptr
+    uint32_t* pair_count;
+    uint32_t pair_cap;
+    uint64_t* block_partials;
+};
+bool wide_supported(int N);
+int wide_slabs(int N);
+int wide_kblocks(int N);
+int wide_trials_per_tile(int N);
+size_t wide_image_bytes(int N, bool lower);
+void wide_build(int N, bool lower, const double* A, const double* c, uint8_t* image, float* c_scaled);
+int wide_grid(uint64_t M, int N, int num_sms);
+cudaError_t wide_launch(const WideLaunch& l, int num_sms, cudaStream_t s);
 
 cudaError_t launch_hist(uint64_t M, const int32_t* S, int nbins, unsigned long long* hist, int num_sms, cudaStream_t s);
 cudaError_t launch_dump(uint64_t M, uint64_t path_offset, uint32_t key0, uint32_t key1, int N,

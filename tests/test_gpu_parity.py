@@ -311,9 +311,11 @@ def test_tensor_kernels_ragged_trial_counts_and_offsets(engine, oracle, N):
 
 
 @pytest.mark.parametrize("N,mode,M", [(160, api.TRANSFORM_LOWER, 20000), (200, api.TRANSFORM_GSL_FULL, 8000),
+                                      (300, api.TRANSFORM_GSL_FULL, 6000), (500, api.TRANSFORM_LOWER, 5000),
                                       (600, api.TRANSFORM_LOWER, 5000), (1024, api.TRANSFORM_LOWER, 1500)])
 def test_large_n_row_slab_tensor_kernel_bit_exact(engine, oracle, N, mode, M):
-    """N > 128 (Stoxx600 shape): tensor-core kernel over row slabs of 256 assets; still bit-exact."""
+    """N > 128 (Stoxx600 shape): the row-slab tensor kernel (N <= 256, N > 640) and the single-pass one (257..640),
+    lower-triangular and dense transforms; still bit-exact."""
     m = synthetic_model(N)
     A = engine.upload_sigma(m.mu, m.Sigma, mode)
     Z, _ = engine.dump_normals(M, 11, path_offset=77)
@@ -348,11 +350,13 @@ def test_slab_fixup_paths_under_a_wide_band():
         "    print(N, r.n_rechecked)\n"
     ) % str(Path(__file__).resolve().parent.parent / "gpu-montecarlo-risk_b200")
     import os, subprocess, sys
-    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MCR_TC_BAND_SCALE="32"), capture_output=True, text=True, timeout=600)
-    assert p.returncode == 0, p.stderr[-2000:]
-    rechecked = {int(l.split()[0]): int(l.split()[1]) for l in p.stdout.strip().splitlines()}
-    assert rechecked[50] > 2000 and rechecked[128] > 5000, rechecked   # the wide band was in force
-    assert rechecked[160] > 400 and rechecked[600] > 2000 and rechecked[1000] > 1000, rechecked
+    for large_n in ("slab", "wide"):   # both kernels for N > 128, at every size (AUTO would pick one per size)
+        p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MCR_TC_BAND_SCALE="32", MCR_LARGE_N=large_n),
+                           capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, (large_n, p.stderr[-2000:])
+        rechecked = {int(l.split()[0]): int(l.split()[1]) for l in p.stdout.strip().splitlines()}
+        assert rechecked[50] > 2000 and rechecked[128] > 5000, rechecked   # the wide band was in force
+        assert rechecked[160] > 400 and rechecked[600] > 2000 and rechecked[1000] > 1000, (large_n, rechecked)
 
 
 def test_error_behaviour():
