@@ -30,6 +30,14 @@ constexpr float BOX_MULLER_ZMAX = 6.8f;
 
 struct u32x4 { uint32_t x, y, z, w; };
 
+// the round keys of Philox4x32-10: k0[r] = key0 + r * W0, k1[r] = key1 + r * W1 (host-computable)
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+    __host__ __device__ void set(uint32_t key0, uint32_t key1) {
+        for (int r = 0; r < 10; ++r) { k0[r] = key0 + (uint32_t)r * PHILOX_W0; k1[r] = key1 + (uint32_t)r * PHILOX_W1; }
+    }
+};
+
 __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -58,6 +66,17 @@ __device__ __forceinline__ void box_muller(uint32_t ua, uint32_t ub, float& za, 
     const float u = __fmaf_rn(__uint2float_rn(ua), 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0, 1]
     const float r = mufu_sqrt(__fmul_rn(-1.3862943611198906f, mufu_lg2(u)));                              // sqrt(-2 ln u)
     const float t = __fmul_rn(__uint2float_rn(ub), 1.4629180792671596e-9f);                               // 2 pi ub 2^-32
+    za = __fmul_rn(r, mufu_cos(t));
+    zb = __fmul_rn(r, mufu_sin(t));
+}
+
+// sqrt(2 ln 2): box_muller's radius is BOX_MULLER_S * sqrt(-lg2 u)
+constexpr double BOX_MULLER_S = 1.1774100225154747;
+// two uniforms -> two standard normals divided by BOX_MULLER_S, and their common radius r' = sqrt(-lg2 u) >= |za'|, |zb'|
+__device__ __forceinline__ void box_muller_raw(uint32_t ua, uint32_t ub, float& za, float& zb, float& r) {
+    const float u = __fmaf_rn(__uint2float_rn(ua), 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0, 1]
+    r = mufu_sqrt(-mufu_lg2(u));
+    const float t = __fmul_rn(__uint2float_rn(ub), 1.4629180792671596e-9f);
     za = __fmul_rn(r, mufu_cos(t));
     zb = __fmul_rn(r, mufu_sin(t));
 }
@@ -156,6 +175,113 @@ struct PhiloxPath {
         const u32x4 u = block(b, k0, k1);
         box_muller(u.x, u.y, z[0], z[1]);
         box_muller(u.z, u.w, z[2], z[3]);
+    }
+    // ---- the same functions with the ten round keys precomputed (PhiloxKeys lives in the kernel parameters, so
+    // every key is a constant-bank operand of its LOP3 and the key schedule costs no instruction) ----
+    __device__ __forceinline__ u32x4 block(uint32_t b, const PhiloxKeys& K) const {
+        const uint64_t p1 = (uint64_t)PHILOX_M1 * b;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ path_hi ^ K.k0[0];
+        const uint32_t n1 = (uint32_t)p1;
+        const uint64_t q0 = (uint64_t)PHILOX_M0 * n0;
+        uint32_t c0 = p1p_hi ^ n1 ^ K.k0[1];
+        uint32_t c1 = p1p_lo;
+        uint32_t c2 = (uint32_t)(q0 >> 32) ^ n3 ^ K.k1[1];
+        uint32_t c3 = (uint32_t)q0;
+#pragma unroll
+        for (int r = 2; r < 10; r++) {
+            const uint64_t a0 = (uint64_t)PHILOX_M0 * c0;
+            const uint64_t a1 = (uint64_t)PHILOX_M1 * c2;
+            const uint32_t m0 = (uint32_t)(a1 >> 32) ^ c1 ^ K.k0[r];
+            const uint32_t m2 = (uint32_t)(a0 >> 32) ^ c3 ^ K.k1[r];
+            c1 = (uint32_t)a1;
+            c3 = (uint32_t)a0;
+            c0 = m0;
+            c2 = m2;
+        }
+        return u32x4{c0, c1, c2, c3};
+    }
+    template <int NB>
+    __device__ __forceinline__ void normals_multi(uint32_t b, const PhiloxKeys& K, float* z) const {
+        uint32_t c0[NB], c1[NB], c2[NB], c3[NB];
+#pragma unroll
+        for (int t = 0; t < NB; ++t) {
+            const uint64_t p1 = (uint64_t)PHILOX_M1 * (b + t);
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ path_hi ^ K.k0[0];
+            const uint32_t n1 = (uint32_t)p1;
+            const uint64_t q0 = (uint64_t)PHILOX_M0 * n0;
+            c0[t] = p1p_hi ^ n1 ^ K.k0[1];
+            c1[t] = p1p_lo;
+            c2[t] = (uint32_t)(q0 >> 32) ^ n3 ^ K.k1[1];
+            c3[t] = (uint32_t)q0;
+        }
+#pragma unroll
+        for (int r = 2; r < 10; r++) {
+#pragma unroll
+            for (int t = 0; t < NB; ++t) {
+                const uint64_t a0 = (uint64_t)PHILOX_M0 * c0[t];
+                const uint64_t a1 = (uint64_t)PHILOX_M1 * c2[t];
+                const uint32_t m0 = (uint32_t)(a1 >> 32) ^ c1[t] ^ K.k0[r];
+                const uint32_t m2 = (uint32_t)(a0 >> 32) ^ c3[t] ^ K.k1[r];
+                c1[t] = (uint32_t)a1;
+                c3[t] = (uint32_t)a0;
+                c0[t] = m0;
+                c2[t] = m2;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NB; ++t) {
+            box_muller(c0[t], c1[t], z[4 * t], z[4 * t + 1]);
+            box_muller(c2[t], c3[t], z[4 * t + 2], z[4 * t + 3]);
+        }
+    }
+    __device__ __forceinline__ void normals(uint32_t b, const PhiloxKeys& K, float z[4]) const {
+        const u32x4 u = block(b, K);
+        box_muller(u.x, u.y, z[0], z[1]);
+        box_muller(u.z, u.w, z[2], z[3]);
+    }
+    // only the first Box-Muller pair of block b (the last asset block of a path when N % 4 is 1 or 2)
+    __device__ __forceinline__ void normals_pair(uint32_t b, const PhiloxKeys& K, float z[2]) const {
+        const u32x4 u = block(b, K);
+        box_muller(u.x, u.y, z[0], z[1]);
+    }
+    // "Raw" flavour for the tensor kernel: z' = z / sqrt(2 ln 2) = sqrt(-lg2 u) (cos t, sin t); the caller folds the factor
+    // into the matrix that multiplies z' (one FMUL per pair less) and bounds |z'| by the largest radius seen, rmax (one
+    // FMNMX3 per Philox block instead of two).  LAST_NORMALS = how many normals of the last block are needed (2 or 4).
+    template <int NB, int LAST_NORMALS = 4>
+    __device__ __forceinline__ void normals_multi_raw(uint32_t b, const PhiloxKeys& K, float* z, float& rmax) const {
+        uint32_t c0[NB], c1[NB], c2[NB], c3[NB];
+#pragma unroll
+        for (int t = 0; t < NB; ++t) {
+            const uint64_t p1 = (uint64_t)PHILOX_M1 * (b + t);
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ path_hi ^ K.k0[0];
+            const uint32_t n1 = (uint32_t)p1;
+            const uint64_t q0 = (uint64_t)PHILOX_M0 * n0;
+            c0[t] = p1p_hi ^ n1 ^ K.k0[1];
+            c1[t] = p1p_lo;
+            c2[t] = (uint32_t)(q0 >> 32) ^ n3 ^ K.k1[1];
+            c3[t] = (uint32_t)q0;
+        }
+#pragma unroll
+        for (int r = 2; r < 10; r++) {
+#pragma unroll
+            for (int t = 0; t < NB; ++t) {
+                const uint64_t a0 = (uint64_t)PHILOX_M0 * c0[t];
+                const uint64_t a1 = (uint64_t)PHILOX_M1 * c2[t];
+                const uint32_t m0 = (uint32_t)(a1 >> 32) ^ c1[t] ^ K.k0[r];
+                const uint32_t m2 = (uint32_t)(a0 >> 32) ^ c3[t] ^ K.k1[r];
+                c1[t] = (uint32_t)a1;
+                c3[t] = (uint32_t)a0;
+                c0[t] = m0;
+                c2[t] = m2;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NB; ++t) {
+            float ra, rb = 0.0f;
+            box_muller_raw(c0[t], c1[t], z[4 * t], z[4 * t + 1], ra);
+            if (t < NB - 1 || LAST_NORMALS > 2) box_muller_raw(c2[t], c3[t], z[4 * t + 2], z[4 * t + 3], rb);
+            rmax = fmaxf(rmax, fmaxf(ra, rb));
+        }
     }
 };
 

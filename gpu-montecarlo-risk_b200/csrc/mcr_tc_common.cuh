@@ -134,6 +134,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 // split 8 normals into fp16 hi + lo and store them as one 16-byte chunk (chunk index c8) of the thread's
 // row in the K-major, 128-byte-swizzled operand images.  zhi_row / zlo_row: shared-space address of the
 // thread's row in K-block 0; r7s = (row % 8) << 4 (the swizzle XOR term).
+template <bool TRACK_ZMAX = true>
 __device__ __forceinline__ void store_chunk(const float (&z)[8], int c8, uint32_t zhi_row, uint32_t zlo_row, uint32_t r7s, float& zmax) {
     using namespace tc;
 #if MCR_TC_ABLATE == 1   // tuning only: RNG without split / store
@@ -145,7 +146,7 @@ __device__ __forceinline__ void store_chunk(const float (&z)[8], int c8, uint32_
     uint32_t hv[4], lv[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        zmax = fmaxf(zmax, fmaxf(fabsf(z[2 * q]), fabsf(z[2 * q + 1])));
+        if (TRACK_ZMAX) zmax = fmaxf(zmax, fmaxf(fabsf(z[2 * q]), fabsf(z[2 * q + 1])));
         const __half2 h = __floats2half2_rn(z[2 * q], z[2 * q + 1]);
         hv[q] = *reinterpret_cast<const uint32_t*>(&h);
         // lo = z - float(hi) in one mixed-precision FMA each (FHFMA: f16 * f16 + f32, exact here)
@@ -156,6 +157,13 @@ __device__ __forceinline__ void store_chunk(const float (&z)[8], int c8, uint32_
     const uint32_t off = (((uint32_t)c8 & 7u) << 4) ^ r7s;   // c8: chunk index inside the K-block
     sts128(zhi_row + off, hv[0], hv[1], hv[2], hv[3]);
     sts128(zlo_row + off, lv[0], lv[1], lv[2], lv[3]);
+}
+
+// an all-zero 16-byte chunk (columns beyond N) in both images
+__device__ __forceinline__ void store_zero_chunk(int c8, uint32_t zhi_row, uint32_t zlo_row, uint32_t r7s) {
+    const uint32_t off = (((uint32_t)c8 & 7u) << 4) ^ r7s;
+    sts128(zhi_row + off, 0u, 0u, 0u, 0u);
+    sts128(zlo_row + off, 0u, 0u, 0u, 0u);
 }
 
 }  // namespace mcr

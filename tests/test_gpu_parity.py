@@ -310,6 +310,22 @@ def test_tensor_kernels_ragged_trial_counts_and_offsets(engine, oracle, N):
     assert engine.run(0, 9, m.x, m.k, kernel=api.KERNEL_TENSOR).n_paths == 0
 
 
+@pytest.mark.parametrize("N", [33, 43, 45, 46, 47, 72, 119])
+def test_tensor_kernel_every_tail_shape(engine, oracle, N):
+    """The last 8-column chunk of a trial row holds N % 8 normals, the constant 1 and zeros, and only the Philox blocks /
+    Box-Muller pairs it needs are drawn (N % 8 = 1..7 take different code paths; 0 is covered by N = 64, 128 above).
+    Enough trials that every warpgroup runs several tiles: all-zero chunks of single-K-block tiles are written once."""
+    m = synthetic_model(N)
+    A = engine.upload_sigma(m.mu, m.Sigma)
+    M = 148 * 6 * 128 * 3 + 77
+    Z, _ = engine.dump_normals(M, 31)
+    ro = oracle.run_normals(A, m.mu, m.k, m.x, Z)
+    r = engine.run(M, 31, m.x, m.k, kernel=api.KERNEL_TENSOR)
+    assert r.kernel == "tensor" and (r.count, r.sum_S, r.n_paths) == (ro["count"], ro["sum_S"], M)
+    h = api.simulate_host(m.mu, A, M, 31, m.x, m.k, a_is_lower=True, want_S_values=True, kernel=api.KERNEL_TENSOR)
+    np.testing.assert_array_equal(h.S_values, ro["S_values"])
+
+
 @pytest.mark.parametrize("N,mode,M", [(160, api.TRANSFORM_LOWER, 20000), (200, api.TRANSFORM_GSL_FULL, 8000),
                                       (300, api.TRANSFORM_GSL_FULL, 6000), (500, api.TRANSFORM_LOWER, 5000),
                                       (600, api.TRANSFORM_LOWER, 5000), (1024, api.TRANSFORM_LOWER, 1500)])
