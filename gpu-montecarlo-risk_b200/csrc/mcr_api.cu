@@ -179,7 +179,7 @@ int mcr_destroy(mcr_engine* e) {
     cudaFree(e->d_flag_list); cudaFree(e->d_flag_count); cudaFree(e->d_accum);
     cudaFree(e->d_block_partials); cudaFree(e->d_partials);
     cudaFree(e->d_port_acc); cudaFree(e->d_port_hist); cudaFree(e->d_port_hist_sum);
-    cudaFree(e->d_hist); cudaFree(e->d_S_tmp);
+    cudaFree(e->d_hist); cudaFree(e->d_S_tmp); cudaFree(e->d_ext_counts); cudaFree(e->d_ext_sums);
     if (e->h_partials) cudaFreeHost(e->h_partials);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -702,6 +702,29 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
     return 0;
 }
 
+// extension accumulators -> the two contiguous partial buffers of mcr_run_async_ext (zeros where not requested)
+__global__ void gather_ext_kernel(const unsigned long long* hist, const double* port_acc, const unsigned long long* port_hist,
+                                  const double* port_hist_sum, int have_hist, int have_port, unsigned long long* counts, double* sums) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < MCR_MAX_HIST) counts[t] = have_hist ? hist[t] : 0ull;
+    if (t == 0) counts[MCR_MAX_HIST] = have_port ? (unsigned long long)(port_acc[0] + 0.5) : 0ull;
+    if (t < 3) sums[t] = have_port ? port_acc[1 + t] : 0.0;
+    if (t < MCR_PORTFOLIO_BINS) {
+        counts[MCR_MAX_HIST + 1 + t] = have_port ? port_hist[t] : 0ull;
+        sums[3 + t] = have_port ? port_hist_sum[t] : 0.0;
+    }
+}
+
+int enqueue_gather_ext(mcr_engine* e, uint64_t* d_ext_counts, double* d_ext_sums, cudaStream_t s) {
+    static_assert(MCR_PORTFOLIO_BINS >= MCR_MAX_HIST, "gather_ext_kernel: one thread per portfolio bin covers hist_S too");
+    gather_ext_kernel<<<(MCR_PORTFOLIO_BINS + 255) / 256, 256, 0, s>>>(
+        e->d_hist, e->d_port_acc, e->d_port_hist, e->d_port_hist_sum, e->last_hist ? 1 : 0, e->last_portfolio ? 1 : 0,
+        reinterpret_cast<unsigned long long*>(d_ext_counts), d_ext_sums);
+    MCR_CUDA(cudaGetLastError());
+    ++e->last_launches;
+    return 0;
+}
+
 void fill_stats(mcr_result* r) {
     const double M = (double)r->n_paths;
     if (r->n_paths == 0) { r->P_hat = r->std_error = r->ci_lower = r->ci_upper = 0.0; return; }
@@ -743,9 +766,36 @@ int mcr_result_from_partials(const uint64_t* h, mcr_result* out) {
 int mcr_run_async(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, double x, int k,
                   const mcr_run_options* opt, uint64_t* d_partials, void* cuda_stream) {
     if (!e || !d_partials) return fail("mcr_run_async: null argument");
-    if (opt && (opt->want_hist || opt->want_portfolio)) return fail("mcr_run_async: extension outputs are only available through mcr_run");
+    if (opt && (opt->want_hist || opt->want_portfolio)) return fail("mcr_run_async: extension outputs need mcr_run_async_ext (or mcr_run)");
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
     return enqueue_run(e, M, path_offset, seed, x, k, opt, nullptr, d_partials, s);
+}
+
+int mcr_run_async_ext(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, double x, int k,
+                      const mcr_run_options* opt, uint64_t* d_partials, uint64_t* d_ext_counts, double* d_ext_sums, void* cuda_stream) {
+    if (!e || !d_partials || !d_ext_counts || !d_ext_sums) return fail("mcr_run_async_ext: null argument");
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+    if (enqueue_run(e, M, path_offset, seed, x, k, opt, nullptr, d_partials, s)) return -1;
+    return enqueue_gather_ext(e, d_ext_counts, d_ext_sums, s);
+}
+
+int mcr_portfolio_hist_range(mcr_engine* e, double* lo, double* hi) {
+    if (!e || !lo || !hi) return fail("mcr_portfolio_hist_range: null argument");
+    if (!e->last_portfolio) return fail("mcr_portfolio_hist_range: the engine's last run had no want_portfolio");
+    *lo = e->port_hist_lo; *hi = e->port_hist_hi;
+    return 0;
+}
+
+int mcr_result_from_partials_ext(const uint64_t* h, const uint64_t* hc, const double* hs, double hist_lo, double hist_hi, mcr_result* out) {
+    if (!hc || !hs) return fail("mcr_result_from_partials_ext: null argument");
+    const int rc = mcr_result_from_partials(h, out);
+    memcpy(out->hist_S, hc, sizeof(uint64_t) * MCR_MAX_HIST);
+    out->portfolio_hits = hc[MCR_MAX_HIST];
+    memcpy(out->portfolio_hist, hc + MCR_MAX_HIST + 1, sizeof(uint64_t) * MCR_PORTFOLIO_BINS);
+    out->portfolio_sum = hs[0]; out->portfolio_sumsq = hs[1]; out->portfolio_tail_loss_sum = hs[2];
+    memcpy(out->portfolio_hist_sum, hs + 3, sizeof(double) * MCR_PORTFOLIO_BINS);
+    out->portfolio_hist_lo = hist_lo; out->portfolio_hist_hi = hist_hi;
+    return rc;
 }
 
 static int finish_sync(mcr_engine* e, mcr_result* out) {

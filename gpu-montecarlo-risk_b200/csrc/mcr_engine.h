@@ -82,6 +82,11 @@ struct mcr_engine {
     int32_t* d_S_tmp = nullptr;
     uint64_t S_tmp_cap = 0;
     bool last_hist = false;
+    // extension partials in the mcr_run_async_ext layout (mcr_simulate_host; allocated on first use)
+    uint64_t* d_ext_counts = nullptr;
+    double* d_ext_sums = nullptr;
+    std::vector<uint64_t> h_ext_counts;
+    std::vector<double> h_ext_sums;
     // last async run bookkeeping
     int last_kernel = 0, last_NT = 0, last_launches = 0;
 };
@@ -92,4 +97,6 @@ namespace mcr {
 int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, double x, int k,
                 const mcr_run_options* opt, const double* dZ, uint64_t* d_out, cudaStream_t s);
 void fill_stats(mcr_result* r);
+// copy the extension accumulators of the run just enqueued on s into the caller's contiguous buffers (device)
+int enqueue_gather_ext(mcr_engine* e, uint64_t* d_ext_counts, double* d_ext_sums, cudaStream_t s);
 }  // namespace mcr

@@ -6,7 +6,8 @@
 //    so a second run_model call pays no cudaMalloc / context cost;
 //  - S_values (M ints, 400 MB at M = 1e8) is produced only when asked for;
 //  - the path range can be sharded over n_gpus devices of this process; the per-device partial
-//    words are combined with ONE NCCL all-reduce (8 x uint64, latency-bound over NVLink).
+//    words are combined with ONE NCCL all-reduce (8 x uint64, latency-bound over NVLink); the extension outputs
+//    (histogram of S, portfolio sums and histogram), when requested, with one more per buffer (uint64 / fp64).
 //    NCCL is resolved with dlopen at first multi-GPU use, so single-GPU users need no libnccl.
 #include "mcr_engine.h"
 
@@ -24,6 +25,7 @@ namespace mcr {
 typedef struct ncclComm* ncclComm_t;
 typedef int ncclResult_t;
 constexpr int kNcclUint64 = 5;
+constexpr int kNcclFloat64 = 8;
 constexpr int kNcclSum = 0;
 struct NcclApi {
     void* lib = nullptr;
@@ -101,6 +103,7 @@ extern "C" int mcr_simulate_host(const mcr_host_request* req, mcr_result* out) {
         acc += m[g];
     }
     int rc = 0;
+    const bool want_ext = req->opt.want_hist || req->opt.want_portfolio;
     auto cleanup = [&]() { for (int g = 0; g < n; ++g) if (dS[g]) { cudaSetDevice(eng[g]->device); cudaFree(dS[g]); } };
 
     for (int g = 0; g < n && !rc; ++g) {
@@ -131,6 +134,15 @@ extern "C" int mcr_simulate_host(const mcr_host_request* req, mcr_result* out) {
         }
         cudaEventRecord(e->ev0, e->stream);
         rc = enqueue_run(e, m[g], off[g], req->seed, req->x, req->k, &o, nullptr, e->d_partials, e->stream);
+        if (!rc && want_ext) {
+            // extension partials of this shard in the all-reducible layout of mcr_run_async_ext
+            if (!e->d_ext_counts && (cudaMalloc(&e->d_ext_counts, sizeof(uint64_t) * MCR_EXT_COUNT_WORDS) != cudaSuccess ||
+                                     cudaMalloc(&e->d_ext_sums, sizeof(double) * MCR_EXT_SUM_WORDS) != cudaSuccess)) {
+                rc = fail("extension partial buffers: allocation failed on device %d", e->device);
+                break;
+            }
+            rc = enqueue_gather_ext(e, e->d_ext_counts, e->d_ext_sums, e->stream);
+        }
     }
     if (n > 1 && !rc) {
         std::vector<ncclComm_t>& comms = g_comms[{req->first_device, n}];
@@ -138,6 +150,12 @@ extern "C" int mcr_simulate_host(const mcr_host_request* req, mcr_result* out) {
         for (int g = 0; g < n; ++g) {
             ncclResult_t r = g_nccl.AllReduce(eng[g]->d_partials, eng[g]->d_partials, MCR_PARTIAL_WORDS, kNcclUint64, kNcclSum, comms[g], eng[g]->stream);
             if (r != 0 && !rc) rc = fail("ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+            if (want_ext) {
+                r = g_nccl.AllReduce(eng[g]->d_ext_counts, eng[g]->d_ext_counts, MCR_EXT_COUNT_WORDS, kNcclUint64, kNcclSum, comms[g], eng[g]->stream);
+                if (r != 0 && !rc) rc = fail("ncclAllReduce (extension counts) failed: %s", g_nccl.GetErrorString(r));
+                r = g_nccl.AllReduce(eng[g]->d_ext_sums, eng[g]->d_ext_sums, MCR_EXT_SUM_WORDS, kNcclFloat64, kNcclSum, comms[g], eng[g]->stream);
+                if (r != 0 && !rc) rc = fail("ncclAllReduce (extension sums) failed: %s", g_nccl.GetErrorString(r));
+            }
         }
         ncclResult_t r = g_nccl.GroupEnd();
         if (r != 0 && !rc) rc = fail("ncclGroupEnd failed: %s", g_nccl.GetErrorString(r));
@@ -150,6 +168,12 @@ extern "C" int mcr_simulate_host(const mcr_host_request* req, mcr_result* out) {
         cudaEventRecord(e->ev1, e->stream);
         cudaMemcpyAsync(e->h_partials, e->d_partials, sizeof(uint64_t) * MCR_PARTIAL_WORDS, cudaMemcpyDeviceToHost, e->stream);
         if (dS[g]) cudaMemcpyAsync(req->S_values_out + off[g], dS[g], sizeof(int32_t) * m[g], cudaMemcpyDeviceToHost, e->stream);
+        if (want_ext && g == 0) {   // after the all-reduce every device holds the totals
+            e->h_ext_counts.resize(MCR_EXT_COUNT_WORDS);
+            e->h_ext_sums.resize(MCR_EXT_SUM_WORDS);
+            cudaMemcpyAsync(e->h_ext_counts.data(), e->d_ext_counts, sizeof(uint64_t) * MCR_EXT_COUNT_WORDS, cudaMemcpyDeviceToHost, e->stream);
+            cudaMemcpyAsync(e->h_ext_sums.data(), e->d_ext_sums, sizeof(double) * MCR_EXT_SUM_WORDS, cudaMemcpyDeviceToHost, e->stream);
+        }
     }
     for (int g = 0; g < n && !rc; ++g) {
         mcr_engine* e = eng[g];
@@ -162,7 +186,9 @@ extern "C" int mcr_simulate_host(const mcr_host_request* req, mcr_result* out) {
         launches += e->last_launches;
     }
     if (!rc) {
-        rc = mcr_result_from_partials(eng[0]->h_partials, out);
+        rc = want_ext ? mcr_result_from_partials_ext(eng[0]->h_partials, eng[0]->h_ext_counts.data(), eng[0]->h_ext_sums.data(),
+                                                     eng[0]->port_hist_lo, eng[0]->port_hist_hi, out)
+                      : mcr_result_from_partials(eng[0]->h_partials, out);
         out->device_ms = ms_max;
         out->kernel_used = eng[0]->last_kernel;
         out->padded_N = eng[0]->last_NT;

@@ -79,7 +79,7 @@ constexpr int TC_UNROLL = MCR_TC_UNROLL;  // 8-normal chunks in flight per gener
 // ~82 instructions per Philox block.  The normals of the fp64 fix-up / dump kernels are unchanged: fl32(s * z') differs
 // from them by a few ulp, far inside the band (2^-19 relative, doubled).
 #ifndef MCR_TC_FOLD
-#define MCR_TC_FOLD 0
+#define MCR_TC_FOLD 1
 #endif
 constexpr bool TC_FOLD = MCR_TC_FOLD != 0;
 constexpr double TC_Z_FACTOR = TC_FOLD ? BOX_MULLER_S : 1.0;   // what the transform columns 0..N-1 are multiplied by

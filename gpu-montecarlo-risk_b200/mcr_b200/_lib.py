@@ -10,6 +10,8 @@ LIB_PATH = Path(os.environ.get("MCR_B200_LIB", PKG_ROOT / "libmcr_b200.so"))  # 
 MCR_MAX_HIST = 1025
 MCR_PORTFOLIO_BINS = 2048
 MCR_PARTIAL_WORDS = 8
+MCR_EXT_COUNT_WORDS = MCR_MAX_HIST + 1 + MCR_PORTFOLIO_BINS
+MCR_EXT_SUM_WORDS = 3 + MCR_PORTFOLIO_BINS
 
 TRANSFORM_LOWER, TRANSFORM_GSL_FULL = 0, 1
 KERNEL_AUTO, KERNEL_FFMA, KERNEL_TENSOR, KERNEL_EXACT = 0, 1, 2, 3
@@ -91,6 +93,10 @@ PROTOTYPES = {
                           C.POINTER(RunOptions), C.POINTER(Result)]),
     "mcr_run_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_int,
                                 C.POINTER(RunOptions), C.c_void_p, C.c_void_p]),
+    "mcr_run_async_ext": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_int,
+                                    C.POINTER(RunOptions), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mcr_portfolio_hist_range": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mcr_result_from_partials_ext": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.POINTER(Result)]),
     "mcr_last_main_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "mcr_result_from_partials": (C.c_int, [C.c_void_p, C.POINTER(Result)]),
     "mcr_run_with_normals": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_int,

@@ -6,8 +6,9 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import (KERNEL_AUTO, KERNEL_EXACT, KERNEL_FFMA, KERNEL_NAMES, KERNEL_TENSOR, MCR_PARTIAL_WORDS,
-                   TRANSFORM_GSL_FULL, TRANSFORM_LOWER, HostRequest, McrError, Result, RunOptions, check)
+from ._lib import (KERNEL_AUTO, KERNEL_EXACT, KERNEL_FFMA, KERNEL_NAMES, KERNEL_TENSOR, MCR_EXT_COUNT_WORDS,
+                   MCR_EXT_SUM_WORDS, MCR_MAX_HIST, MCR_PARTIAL_WORDS, TRANSFORM_GSL_FULL, TRANSFORM_LOWER, HostRequest,
+                   McrError, Result, RunOptions, check)
 
 
 def _f64(a):
@@ -138,6 +139,20 @@ class Engine:
         check(self._lib.mcr_run_async(self._h, int(M), int(path_offset), int(seed), float(x), int(k), C.byref(o),
                                       C.c_void_p(int(d_partials_ptr)), C.c_void_p(int(stream_ptr) if stream_ptr else None)))
 
+    def run_async_ext(self, M, seed, x, k, d_partials_ptr, d_ext_counts_ptr, d_ext_sums_ptr, stream_ptr, path_offset=0,
+                      kernel=KERNEL_AUTO, portfolio_threshold=None, want_hist=False):
+        """run_async plus the extension partials of this shard (histogram of S, portfolio sums and histogram) in two
+        caller-owned device buffers of MCR_EXT_COUNT_WORDS uint64 / MCR_EXT_SUM_WORDS float64 plain sums."""
+        o = make_options(kernel, False, portfolio_threshold=portfolio_threshold, want_hist=want_hist)
+        check(self._lib.mcr_run_async_ext(self._h, int(M), int(path_offset), int(seed), float(x), int(k), C.byref(o),
+                                          C.c_void_p(int(d_partials_ptr)), C.c_void_p(int(d_ext_counts_ptr)),
+                                          C.c_void_p(int(d_ext_sums_ptr)), C.c_void_p(int(stream_ptr) if stream_ptr else None)))
+
+    def portfolio_hist_range(self):
+        lo, hi = C.c_double(), C.c_double()
+        check(self._lib.mcr_portfolio_hist_range(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def run_with_normals(self, Z, x, k, kernel=KERNEL_AUTO, no_recheck=False, want_S=True) -> RunResult:
         Z = _f64(Z)
         M = Z.shape[0]
@@ -184,9 +199,26 @@ def result_from_partials(words) -> RunResult:
     return RunResult.from_c(r)
 
 
+def result_from_partials_ext(words, ext_counts, ext_sums, hist_range=(0.0, 0.0), N=None, portfolio=False) -> RunResult:
+    """Result of (all-reduced) partial words plus extension partials: .hist_S and, with portfolio=True, .portfolio."""
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    c = np.ascontiguousarray(ext_counts, dtype=np.uint64)
+    s = np.ascontiguousarray(ext_sums, dtype=np.float64)
+    assert w.size == MCR_PARTIAL_WORDS and c.size == MCR_EXT_COUNT_WORDS and s.size == MCR_EXT_SUM_WORDS
+    r = Result()
+    check(_lib.load().mcr_result_from_partials_ext(w.ctypes.data, c.ctypes.data, s.ctypes.data, float(hist_range[0]),
+                                                   float(hist_range[1]), C.byref(r)))
+    res = RunResult.from_c(r)
+    res.hist_S = np.ctypeslib.as_array(r.hist_S)[: (N + 1) if N is not None else MCR_MAX_HIST].astype(np.int64)
+    if portfolio:
+        res.portfolio = portfolio_outputs(r)
+    return res
+
+
 def simulate_host(mu, A, M, seed, x, k, a_is_lower=False, n_gpus=1, first_device=0, want_S_values=False,
-                  kernel=KERNEL_AUTO, no_recheck=False, reupload=False) -> RunResult:
-    """The one-shot call the C plugin makes: host buffers in, result (and optional S_values) out."""
+                  kernel=KERNEL_AUTO, no_recheck=False, reupload=False, portfolio_threshold=None, want_hist=False) -> RunResult:
+    """The one-shot call the C plugin makes: host buffers in, result (and optional S_values) out.  The extension outputs
+    (want_hist, portfolio_threshold; equal weights) are combined over n_gpus devices like the counts."""
     mu, A = _f64(mu), _f64(A)
     req = HostRequest()
     req.struct_size = C.sizeof(HostRequest)
@@ -197,7 +229,12 @@ def simulate_host(mu, A, M, seed, x, k, a_is_lower=False, n_gpus=1, first_device
     req.want_S_values = int(bool(want_S_values))
     req.reupload = int(bool(reupload))
     req.S_values_out = S.ctypes.data if want_S_values else None
-    req.opt = make_options(kernel, no_recheck)
+    req.opt = make_options(kernel, no_recheck, portfolio_threshold=portfolio_threshold, want_hist=want_hist)
     r = Result()
     check(_lib.load().mcr_simulate_host(C.byref(req), C.byref(r)))
-    return RunResult.from_c(r, S)
+    res = RunResult.from_c(r, S)
+    if portfolio_threshold is not None:
+        res.portfolio = portfolio_outputs(r)
+    if want_hist:
+        res.hist_S = np.ctypeslib.as_array(r.hist_S)[: mu.shape[0] + 1].astype(np.int64)
+    return res

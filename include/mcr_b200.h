@@ -121,6 +121,23 @@ int mcr_last_main_kernel_ms(mcr_engine *e, float *avg_ms_per_launch, int *n_laun
 /* Turn (possibly all-reduced) partial words copied to the host into a result with the reference's statistics. */
 int mcr_result_from_partials(const uint64_t *h_partials, mcr_result *out);
 
+/* Extension outputs (want_hist / want_portfolio) of a shard, for callers that combine shards themselves: same as
+ * mcr_run_async, and the extension partials of the run are left in two DEVICE buffers of plain sums, so the
+ * cross-GPU step is one more sum-allreduce per buffer (uint64 and fp64):
+ *   d_ext_counts[MCR_EXT_COUNT_WORDS] uint64: hist_S[0..MCR_MAX_HIST) | portfolio_hits | portfolio_hist[0..BINS)
+ *   d_ext_sums[MCR_EXT_SUM_WORDS]     fp64  : sum w.R, sum (w.R)^2, tail-loss sum | portfolio_hist_sum[0..BINS)
+ * Parts that were not requested are zero.  The portfolio histogram range depends on the model and the weights only
+ * (w.mu +- 8 sigma_p), so every shard bins identically; mcr_portfolio_hist_range returns it after the run was enqueued. */
+#define MCR_EXT_COUNT_WORDS (MCR_MAX_HIST + 1 + MCR_PORTFOLIO_BINS)
+#define MCR_EXT_SUM_WORDS (3 + MCR_PORTFOLIO_BINS)
+int mcr_run_async_ext(mcr_engine *e, uint64_t M, uint64_t path_offset, uint64_t seed, double x, int k,
+                      const mcr_run_options *opt, uint64_t *d_partials, uint64_t *d_ext_counts, double *d_ext_sums,
+                      void *cuda_stream);
+int mcr_portfolio_hist_range(mcr_engine *e, double *lo, double *hi);
+/* mcr_result_from_partials plus the extension fields, from (possibly all-reduced) host copies of the three buffers. */
+int mcr_result_from_partials_ext(const uint64_t *h_partials, const uint64_t *h_ext_counts, const double *h_ext_sums,
+                                 double portfolio_hist_lo, double portfolio_hist_hi, mcr_result *out);
+
 /* Parity entry point (the model interface has no "feed normals" hook):
  * same correlate/threshold/reduce code, normals supplied by the caller instead of Philox.
  * Z: HOST pointer, M x N row-major fp64 (the layout serial.c:67-69 fills, one trial per row). */

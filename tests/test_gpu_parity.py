@@ -284,6 +284,54 @@ def test_histogram_of_crash_counts(engine, oracle):
             assert int(r.hist_S[k:].sum()) == r.count and int((np.arange(N + 1) * r.hist_S).sum()) == r.sum_S
 
 
+def test_extension_partials_shard_like_the_counts(engine, oracle):
+    """mcr_run_async_ext leaves the extension outputs of a shard as plain sums in two device buffers; adding the buffers of
+    the shards of a path range (what a sum-allreduce across GPUs does) must reproduce mcr_run over the whole range:
+    integer parts (histogram of S, portfolio hits and histogram) exactly, the sums to 1e-6 relative, per-bin sums and ES to
+    1e-4 (they are staged per CTA with fp32 shared-memory atomics, whose grouping changes with the shard boundaries).  mcr_simulate_host carries the same outputs."""
+    import torch
+    N = 50
+    mu, Sigma, x, k = model(N)
+    A = engine.upload_sigma(mu, Sigma)
+    M, seed, xp = 700001, 77, 0.015
+    whole = engine.run(M, seed, x, k, portfolio_threshold=xp, want_hist=True)
+    stream = torch.cuda.Stream()
+    words = torch.zeros(api.MCR_PARTIAL_WORDS, dtype=torch.int64, device="cuda")
+    counts = torch.zeros(api.MCR_EXT_COUNT_WORDS, dtype=torch.int64, device="cuda")
+    sums = torch.zeros(api.MCR_EXT_SUM_WORDS, dtype=torch.float64, device="cuda")
+    tw, tc, ts = torch.zeros_like(words), torch.zeros_like(counts), torch.zeros_like(sums)
+    cuts = [0, 1, 250000, 250128, M]
+    with torch.cuda.stream(stream):
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            engine.run_async_ext(b - a, seed, x, k, words.data_ptr(), counts.data_ptr(), sums.data_ptr(), stream.cuda_stream,
+                                 path_offset=a, portfolio_threshold=xp, want_hist=True)
+            tw += words; tc += counts; ts += sums
+    stream.synchronize()
+    r = api.result_from_partials_ext(tw.cpu().numpy().astype(np.uint64), tc.cpu().numpy().astype(np.uint64), ts.cpu().numpy(),
+                                     engine.portfolio_hist_range(), N=N, portfolio=True)
+    assert (r.n_paths, r.count, r.sum_S) == (M, whole.count, whole.sum_S)
+    np.testing.assert_array_equal(r.hist_S, whole.hist_S)
+    pw, pr = whole.portfolio, r.portfolio
+    assert pr["hits"] == pw["hits"] and (pr["hist_lo"], pr["hist_hi"]) == (pw["hist_lo"], pw["hist_hi"])
+    np.testing.assert_array_equal(pr["hist"], pw["hist"])
+    np.testing.assert_allclose(pr["hist_sum"], pw["hist_sum"], rtol=1e-4, atol=1e-7)
+    for key in ("mean", "var", "tail_loss_sum"):
+        assert pr[key] == pytest.approx(pw[key], rel=1e-6)
+    for a in (0.95, 0.99):
+        assert pr["VaR"][a] == pytest.approx(pw["VaR"][a], rel=1e-6) and pr["ES"][a] == pytest.approx(pw["ES"][a], rel=1e-4)
+    # without the extension flags the buffers come back zero
+    engine.run_async_ext(1000, seed, x, k, words.data_ptr(), counts.data_ptr(), sums.data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    assert int(counts.abs().sum()) == 0 and float(sums.abs().sum()) == 0.0 and int(words[0]) == 1000
+    # one-shot host entry point
+    h = api.simulate_host(mu, A, M, seed, x, k, a_is_lower=True, portfolio_threshold=xp, want_hist=True)
+    assert (h.count, h.sum_S) == (whole.count, whole.sum_S)
+    np.testing.assert_array_equal(h.hist_S, whole.hist_S)
+    assert h.portfolio["hits"] == pw["hits"]
+    np.testing.assert_array_equal(h.portfolio["hist"], pw["hist"])
+    assert h.portfolio["VaR"][0.99] == pytest.approx(pw["VaR"][0.99], rel=1e-6)
+
+
 def test_kernel_selection(engine):
     mu, Sigma, x, k = model(15)
     engine.upload_sigma(mu, Sigma)
