@@ -31,6 +31,11 @@
 
 namespace mcr {
 
+// tuning only (tools/devbuild.sh): 1 = the loader copies each ring slot once and then only signals it (no transform stream),
+// 2 = the generators skip Philox / Box-Muller (stale Z), 3 = the MMA warp commits without issuing MMAs.  Results are garbage.
+#ifndef MCR_WIDE_ABLATE
+#define MCR_WIDE_ABLATE 0
+#endif
 constexpr int WIDE_GEN_THREADS = 512;
 constexpr int WIDE_THREADS = WIDE_GEN_THREADS + 64;       // + warp 16: MMA issue, warp 17: transform loader
 // transform blocks in flight: what shared memory allows next to the two Z slots (the stream from L2 is latency-bound)
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
                         const uint32_t bhi = smem_u32(s_ring + rs * WIDE_BLOCK_BYTES), blo = bhi + 128 * 128;
                         const uint32_t d_tmem = tmem_base + (uint32_t)t * NT;
 #pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
+                        for (int pass = 0; pass < (MCR_WIDE_ABLATE == 3 ? 0 : 3); ++pass) {
                             const uint32_t ba = pass == 1 ? blo : bhi;   // transform: hi, lo, hi
                             const uint32_t za = pass == 2 ? zlo : zhi;   // normals:   hi, hi, lo
 #pragma unroll
@@ -170,6 +175,10 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
                     for (int t = p.lower ? (kb >> 1) : 0; t < NSLAB; ++t, ++blk, ++idx) {
                         const uint32_t rs = blk % WIDE_RING;
                         if (blk >= WIDE_RING) mbar_wait(&s_bempty[rs], ((blk / WIDE_RING) - 1u) & 1u);
+                        if (MCR_WIDE_ABLATE == 1 && blk >= WIDE_RING) {
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_bfull[rs])) : "memory");
+                            continue;
+                        }
                         mbar_expect_tx(&s_bfull[rs], WIDE_BLOCK_BYTES);
                         bulk_g2s(smem_u32(s_ring + rs * WIDE_BLOCK_BYTES), p.image + (size_t)idx * WIDE_BLOCK_BYTES, WIDE_BLOCK_BYTES,
                                  &s_bfull[rs]);
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
                 const uint32_t slot = ukb & 1u;
                 // every thread (also the ones that generate nothing) stays within two K-blocks of the MMA warp
                 if (ukb >= 2) mbar_wait<64>(&s_zempty[slot], ((ukb >> 1) - 1u) & 1u);
-                if (active) {
+                if (active && !(MCR_WIDE_ABLATE == 2 && ukb >= 2)) {
                     const int col0 = KBLOCK * kb + PCOLS * part;
                     float z[PCOLS];
                     if (col0 + PCOLS <= p.N) {

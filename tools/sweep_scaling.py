@@ -19,7 +19,7 @@ eng = api.Engine(local)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 partials = torch.zeros(api.MCR_PARTIAL_WORDS, dtype=torch.int64, device="cuda")
 # rough single-GPU rates (sims/s) to keep each point under a few seconds
-RATE = {16: 5e10, 32: 2e10, 64: 8e9, 100: 6e9, 128: 4e9, 256: 6e8, 512: 1.5e8, 600: 1.9e8, 1024: 2.5e7}
+RATE = {16: 5e10, 32: 2e10, 64: 1.2e10, 100: 8e9, 128: 5e9, 256: 2e9, 512: 6e8, 600: 5e8, 1024: 2.4e8}
 rows = []
 for N in (16, 32, 64, 128, 256, 512, 1024, 100, 600):
     m = synthetic_model(N)

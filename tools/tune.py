@@ -43,6 +43,9 @@ if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 50
     M = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000_000
     libs = sorted((ROOT / "devlibs").glob("*/libmcr_b200.so"))
+    if os.environ.get("MCR_TUNE_LIBS"):   # comma-separated subset of devlibs/<name>
+        keep = set(os.environ["MCR_TUNE_LIBS"].split(","))
+        libs = [l for l in libs if l.parent.name in keep]
     ref = None
     for lib in libs:
         env = dict(os.environ, MCR_B200_LIB=str(lib))
