@@ -309,10 +309,12 @@ def main():
                    "api": "mcr_simulate_host (host mu/A in, result out; S_values not requested, as the plugin's default)"}
         peak_tf = eng.measure_fp32_peak(20.0)
         nominal_tf = 148 * 128 * 2 * (clocks.max_mhz or 1965) * 1e6 / 1e12
-        sims_per_launch = min(M, 1 << 27)
+        # k_ms is the average over the path-kernel launches of a step (a step of more than one chunk - 2^27 trials, 2^24 on the
+        # N > 128 kernels - is several launches): trials per launch = the step's trials / launches
+        sims_per_launch = M / max(1, launches_per_kernel_step)
         achieved_tf = sims_per_launch * flops_per_sim(N) / (k_ms * 1e-3) / 1e12
         tensor = None
-        if one.kernel == "tensor":
+        if one.kernel == "tensor" and N <= 128:
             # what the tensor pipe actually executes: 3 passes (fp16 hi/lo split) over the padded dense tile
             kpad = 64 * ((N + 1 + 63) // 64)
             exec_tf = sims_per_launch * 3 * 2 * one.padded_N * kpad / (k_ms * 1e-3) / 1e12
@@ -322,7 +324,8 @@ def main():
                       "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, of measured)" if mp.exists() else "fallback 1.59 PFLOP/s (of fallback)",
                       "note": "the correlate runs on tcgen05 (fp16x3, fp32 accumulate in TMEM); the kernel is bound by the Philox/Box-Muller "
                               "instruction stream, not by the tensor pipe"}
-        kname = (f"tc_path_kernel<NOUT={one.padded_N}> (tcgen05 fp16x3 correlate)" if one.kernel == "tensor"
+        kname = ("tc_wide_kernel / tc_slab_kernel (tcgen05 fp16x3 correlate, N > 128: see DESIGN.md section 3)" if one.kernel == "tensor" and N > 128
+                 else f"tc_path_kernel<NOUT={one.padded_N}> (tcgen05 fp16x3 correlate)" if one.kernel == "tensor"
                  else f"ffma_path_kernel<NT={one.padded_N},LOWER,philox>")
         roof = {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf if peak_tf else None,

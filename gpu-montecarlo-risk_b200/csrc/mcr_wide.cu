@@ -38,8 +38,36 @@ namespace mcr {
 #endif
 constexpr int WIDE_GEN_THREADS = 512;
 constexpr int WIDE_THREADS = WIDE_GEN_THREADS + 64;       // + warp 16: MMA issue, warp 17: transform loader
-// transform blocks in flight: what shared memory allows next to the two Z slots (the stream from L2 is latency-bound)
-__host__ __device__ constexpr int wide_ring(int nt) { return nt >= 128 ? 4 : 5; }
+// Shared memory is split between Z slots (K-blocks of normals the generators may be ahead of the tensor core) and the ring of
+// transform blocks in flight from L2.  Z slot = NT * 256 B, transform block = 32 KB; ~221 KB usable next to the static part.
+// Measured (profiles/r01_wide_zslots_early_epilogue.log): depth matters little — every combination is within 3 % — because
+// the MMAs are bound by shared-memory operand bandwidth, not by hand-over stalls; the defaults are the fastest combination.
+#ifndef MCR_WIDE_ZSLOTS_128
+#define MCR_WIDE_ZSLOTS_128 3
+#endif
+#ifndef MCR_WIDE_RING_128
+#define MCR_WIDE_RING_128 3
+#endif
+#ifndef MCR_WIDE_ZSLOTS_96
+#define MCR_WIDE_ZSLOTS_96 5
+#endif
+#ifndef MCR_WIDE_RING_96
+#define MCR_WIDE_RING_96 3
+#endif
+#ifndef MCR_WIDE_ZSLOTS_64
+#define MCR_WIDE_ZSLOTS_64 6
+#endif
+#ifndef MCR_WIDE_RING_64
+#define MCR_WIDE_RING_64 3
+#endif
+// Lower-triangular transform: slab t (last MMAs in K-block 2t + 1) is thresholded and re-initialised inside the K loop, before
+// the generators start K-block 2t + 1 + MCR_WIDE_ELAG; 0 = every slab at the tile boundary.
+#ifndef MCR_WIDE_ELAG
+#define MCR_WIDE_ELAG 3
+#endif
+__host__ __device__ constexpr int wide_zslots(int nt) { return nt >= 128 ? MCR_WIDE_ZSLOTS_128 : nt >= 96 ? MCR_WIDE_ZSLOTS_96 : MCR_WIDE_ZSLOTS_64; }
+__host__ __device__ constexpr int wide_ring(int nt) { return nt >= 128 ? MCR_WIDE_RING_128 : nt >= 96 ? MCR_WIDE_RING_96 : MCR_WIDE_RING_64; }
+constexpr int WIDE_BAR_ACC = 8, WIDE_BAR_GEN = 9;         // named barriers: 1 .. ZS = Z slot full, accumulators ready, generator sync
 constexpr uint32_t WIDE_BLOCK_BYTES = 2 * 128 * 128;       // 128 rows x 64 columns, fp16 hi + lo
 
 struct WideParams {
@@ -100,13 +128,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
     constexpr int G32 = NT / 32;                       // 32-trial column groups
     constexpr int ALL = WIDE_GEN_THREADS + 32;         // generators + MMA warp (named barriers 1..3)
     constexpr int MMA_WARP = WIDE_GEN_THREADS / 32, LOAD_WARP = MMA_WARP + 1;
-    constexpr int WIDE_RING = wide_ring(NT);
+    constexpr int WIDE_RING = wide_ring(NT), ZS = wide_zslots(NT);
+    static_assert(ZS >= 2 && ZS <= 7, "Z slots use named barriers 1 .. ZS");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* s_z = smem;                   // [2][hi | lo][NT x 128 B]
-    uint8_t* s_ring = smem + 2 * ZSLOT;    // [WIDE_RING][hi | lo][128 x 128 B]
-    __shared__ uint64_t s_zempty[2], s_bfull[WIDE_RING], s_bempty[WIDE_RING], s_done;
+    uint8_t* s_z = smem;                   // [ZS][hi | lo][NT x 128 B]
+    uint8_t* s_ring = smem + ZS * ZSLOT;   // [WIDE_RING][hi | lo][128 x 128 B]
+    __shared__ uint64_t s_zempty[ZS], s_bfull[WIDE_RING], s_bempty[WIDE_RING], s_done, s_slabdone[WIDE_MAX_SLABS];
     __shared__ uint32_t s_tmem;
     __shared__ float s_zsq[8][128];
     __shared__ uint32_t s_S[128], s_namb[128], s_amb[128];
@@ -114,8 +143,9 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int b = 0; b < 2; ++b) mbar_init(&s_zempty[b], 1);
+        for (int b = 0; b < ZS; ++b) mbar_init(&s_zempty[b], 1);
         for (int b = 0; b < WIDE_RING; ++b) { mbar_init(&s_bfull[b], 1); mbar_init(&s_bempty[b], 1); }
+        for (int b = 0; b < WIDE_MAX_SLABS; ++b) mbar_init(&s_slabdone[b], 1);
         mbar_init(&s_done, 1);
     }
     if (tid < 128) { s_S[tid] = 0u; s_namb[tid] = 0u; s_amb[tid] = 0u; }
@@ -130,17 +160,27 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
     const uint64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int KBN = p.kbn, NSLAB = p.nslab;
     uint32_t cnt = 0, sum_s = 0;
+    // With a lower-triangular transform slab t receives its last MMAs in K-block 2t + 1 (the MMA warp then commits
+    // s_slabdone[t]).  Slabs 0 .. n_early - 1 are thresholded and re-initialised by the generator warps inside the K loop,
+    // before they start K-block 2t + 1 + ELAG, while the tensor core works on the other slabs; the remaining slab(s) are left
+    // for the tile boundary, after the generators have queued K-blocks 0 .. kb_boundary of the next tile.  The MMA warp starts
+    // the next tile on the early slabs (their re-initialisation precedes, in the program order of every generator thread,
+    // the hand-over of the next tile's first Z K-block) and waits for the boundary slabs only when it reaches them.
+    constexpr int ELAG = MCR_WIDE_ELAG;
+    const int n_early = (ELAG > 0 && p.lower && KBN - 2 - ELAG >= 0) ? min((KBN - 2 - ELAG) / 2 + 1, NSLAB - 1) : 0;
+    const int kb_boundary = min(min(ZS - 1, ELAG > 0 ? ELAG : ZS - 1), KBN - 1);
 
     if (warp == MMA_WARP) {
         // ---- MMA issue: K-blocks in order; for each, the slabs that need it, as their transform blocks arrive ----
         uint32_t ukb = 0, blk = 0;
         for (uint64_t n = 0; n < my_tiles; ++n) {
-            named_bar_sync(3, ALL);          // accumulators initialised (and the previous tile's epilogue is done with them)
             for (int kb = 0; kb < KBN; ++kb, ++ukb) {
-                const uint32_t slot = ukb & 1u;
+                const uint32_t slot = ukb % ZS;
                 named_bar_sync(1 + slot, ALL);   // Z K-block complete and visible to the async proxy
                 const uint32_t zhi = smem_u32(s_z + slot * ZSLOT), zlo = zhi + NT * 128;
                 for (int t = p.lower ? (kb >> 1) : 0; t < NSLAB; ++t, ++blk) {
+                    // slabs n_early .. : initialised (and the previous tile's epilogue is done with them)
+                    if (kb == 0 && t == n_early) named_bar_sync(WIDE_BAR_ACC, ALL);
                     const uint32_t rs = blk % WIDE_RING;
                     mbar_wait(&s_bfull[rs], (blk / WIDE_RING) & 1u);
                     if (lane == 0) {
@@ -159,7 +199,10 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
                     }
                     __syncwarp();
                 }
-                if (lane == 0) umma_commit(&s_zempty[slot]);
+                if (lane == 0) {
+                    umma_commit(&s_zempty[slot]);
+                    if ((kb & 1) && (kb >> 1) < n_early) umma_commit(&s_slabdone[kb >> 1]);
+                }
                 __syncwarp();
             }
             if (lane == 0) umma_commit(&s_done);
@@ -207,14 +250,16 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
             }
             tmem_st_wait();
             tc_fence_before();
-            named_bar_arrive(3, ALL);
+            named_bar_arrive(WIDE_BAR_ACC, ALL);
         };
 
-        auto epilogue = [&](uint64_t i0, float zsq, bool last) {
+        // Threshold + count the accumulators of slabs [t0, t1) into the per-trial shared-memory state (s_S, s_namb, s_amb) and,
+        // with reinit, hand each 32 x 32 piece back initialised for the next tile.  zsq = the thread's running sum of squares:
+        // the columns generated so far cover every column these slabs have multiplied.  The caller guarantees that the MMAs
+        // of the slabs are complete (mbarrier wait).
+        auto slab_epilogue = [&](int t0, int t1, float zsq, bool reinit) {
             if (active) s_zsq[part][trial] = zsq;
-            named_bar_sync(4, WIDE_GEN_THREADS);
-            mbar_wait<64>(&s_done, done_parity);
-            done_parity ^= 1u;
+            named_bar_sync(WIDE_BAR_GEN, WIDE_GEN_THREADS);
             tc_fence_after();
             float zn[G32], znmax = 0.0f;
 #pragma unroll
@@ -222,7 +267,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
                 float s = 0.0f;
 #pragma unroll
                 for (int q = 0; q < PARTS; ++q) s += s_zsq[q][32 * g + lane];
-                zn[g] = sqrtf(s) * 1.0001f;      // ||z||_2 of trial 32 g + lane (all N columns: an upper bound for every slab)
+                zn[g] = sqrtf(s) * 1.0001f;      // ||z||_2 of trial 32 g + lane over the columns so far
                 znmax = fmaxf(znmax, zn[g]);
             }
             znmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(znmax)));
@@ -230,8 +275,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
 #pragma unroll
             for (int g = 0; g < G32; ++g) Sloc[g] = 0u;
 #pragma unroll 1
-            for (int pc = wq; pc < NSLAB * G32; pc += 4) {
-                const int t = pc / G32, g = pc - t * G32;
+            for (int pc = wq; pc < (t1 - t0) * G32; pc += 4) {
+                const int t = t0 + pc / G32, g = pc % G32;
                 const float dr = p.delta_rel[t], da = p.delta_abs[t];
                 const float thr_max = __fmaf_rn(dr, znmax, da);
                 uint32_t v[32];
@@ -275,12 +320,19 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
                         }
                     }
                 }
+                if (reinit)   // the piece is read: give it back holding (mu_i + x) * 2^10 of this lane's row for the next tile
+                    tmem_st32_bcast(taddr_q + (uint32_t)(t * NT + 32 * g), __float_as_uint(__ldg(p.c_scaled + t * 128 + quarter * 32 + lane)));
             }
 #pragma unroll
             for (int g = 0; g < G32; ++g)
                 if (Sloc[g]) atomicAdd(&s_S[32 * g + lane], Sloc[g]);
+            if (reinit) tmem_st_wait();
             tc_fence_before();
-            named_bar_sync(4, WIDE_GEN_THREADS);
+            named_bar_sync(WIDE_BAR_GEN, WIDE_GEN_THREADS);   // s_S / s_namb / s_amb are complete for these slabs; s_zsq may be rewritten
+        };
+
+        // the trials of a finished tile: counts, or the fix-up lists when a decision was near the threshold
+        auto finish_tile = [&](uint64_t i0) {
             if (tid < NT) {
                 const uint64_t i = i0 + tid;
                 const uint32_t S = s_S[tid], n_amb = s_namb[tid], amb = s_amb[tid];
@@ -301,7 +353,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
                     }
                 }
             }
-            if (!last) init_accumulators();
+        };
+
+        auto boundary_epilogue = [&](uint64_t i0, float zsq, bool last) {
+            mbar_wait<64>(&s_done, done_parity);
+            done_parity ^= 1u;
+            slab_epilogue(n_early, NSLAB, zsq, !last);
+            if (!last) named_bar_arrive(WIDE_BAR_ACC, ALL);   // every slab is initialised again (tcgen05.st waited for, fenced)
+            finish_tile(i0);
         };
 
         if (my_tiles > 0) init_accumulators();
@@ -316,9 +375,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
             float zsq = 0.0f;
 #pragma unroll 1
             for (int kb = 0; kb < KBN; ++kb, ++ukb) {
-                const uint32_t slot = ukb & 1u;
-                // every thread (also the ones that generate nothing) stays within two K-blocks of the MMA warp
-                if (ukb >= 2) mbar_wait<64>(&s_zempty[slot], ((ukb >> 1) - 1u) & 1u);
+                const uint32_t slot = ukb % ZS;
+                // every thread (also the ones that generate nothing) stays within ZS K-blocks of the MMA warp
+                if (ukb >= (uint32_t)ZS) mbar_wait<64>(&s_zempty[slot], ((ukb / ZS) - 1u) & 1u);
+                if (ELAG > 0 && kb >= 1 + ELAG && ((kb - 1 - ELAG) & 1) == 0 && (kb - 1 - ELAG) / 2 < n_early) {
+                    const int t = (kb - 1 - ELAG) / 2;
+                    mbar_wait<64>(&s_slabdone[t], (uint32_t)(n & 1u));
+                    slab_epilogue(t, t + 1, zsq, n + 1 < my_tiles);
+                }
                 if (active && !(MCR_WIDE_ABLATE == 2 && ukb >= 2)) {
                     const int col0 = KBLOCK * kb + PCOLS * part;
                     float z[PCOLS];
@@ -348,13 +412,13 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
                 }
                 fence_async_smem();
                 named_bar_arrive(1 + slot, ALL);
-                // the previous tile's epilogue, once two K-blocks of this tile are queued for the tensor core
-                if (kb == 1 && n > 0) epilogue(prev_i0, prev_zsq, false);
+                // the previous tile's last slab(s), once K-blocks 0 .. kb_boundary of this tile are queued for the tensor core
+                if (kb == kb_boundary && n > 0) boundary_epilogue(prev_i0, prev_zsq, false);
             }
             prev_i0 = i0;
             prev_zsq = zsq;
         }
-        if (my_tiles > 0) epilogue(prev_i0, prev_zsq, true);
+        if (my_tiles > 0) boundary_epilogue(prev_i0, prev_zsq, true);
         if (tid < NT) {
             cnt = __reduce_add_sync(0xffffffffu, cnt);
             sum_s = __reduce_add_sync(0xffffffffu, sum_s);
@@ -414,7 +478,7 @@ void wide_build(int N, bool lower, const double* A, const double* c, uint8_t* im
 
 template <int NT>
 static cudaError_t wide_launch_nt(const WideParams& p, int num_sms, cudaStream_t s) {
-    const size_t smem = 2 * (size_t)(2 * NT * 128) + (size_t)wide_ring(NT) * WIDE_BLOCK_BYTES + 1024;
+    const size_t smem = (size_t)wide_zslots(NT) * (size_t)(2 * NT * 128) + (size_t)wide_ring(NT) * WIDE_BLOCK_BYTES + 1024;
     cudaError_t e = cudaFuncSetAttribute(tc_wide_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint64_t tiles = (p.M + NT - 1) / NT;

@@ -397,6 +397,24 @@ def test_large_n_row_slab_tensor_kernel_bit_exact(engine, oracle, N, mode, M):
         engine.run(1000, 11, m.x, m.k, kernel=api.KERNEL_FFMA)
 
 
+@pytest.mark.parametrize("N,mode,tiles", [(320, api.TRANSFORM_LOWER, 3), (600, api.TRANSFORM_LOWER, 3), (300, api.TRANSFORM_GSL_FULL, 2)])
+def test_single_pass_kernel_several_tiles_per_cta(engine, oracle, N, mode, tiles):
+    """The single-pass kernel (257 <= N <= 640) pipelines across the tiles of a CTA: with a lower-triangular transform a slab
+    is thresholded and re-initialised inside the K loop as soon as its last K-block is done, the last slab(s) at the tile
+    boundary while the next tile's first K-blocks are generated.  Enough trials for several tiles per CTA plus a ragged one;
+    per-trial S identical to the oracle."""
+    m = synthetic_model(N)
+    A = engine.upload_sigma(m.mu, m.Sigma, mode)
+    nt = 128 if N <= 512 else 96
+    M = 148 * nt * tiles + nt + 5
+    Z, _ = engine.dump_normals(M, 13)
+    ro = oracle.run_normals(A, m.mu, m.k, m.x, Z)
+    h = api.simulate_host(m.mu, A, M, 13, m.x, m.k, a_is_lower=(mode == api.TRANSFORM_LOWER), want_S_values=True)
+    assert h.kernel == "tensor"
+    np.testing.assert_array_equal(h.S_values, ro["S_values"])
+    assert (h.count, h.sum_S) == (ro["count"], ro["sum_S"])
+
+
 def test_slab_fixup_paths_under_a_wide_band():
     """The tensor kernels have two fix-ups: a single near-threshold decision is re-evaluated alone (exact_pairs_kernel), a
     trial with several goes to the full fp64 kernel.  A band widened 32x (env knob, read once per process) makes both

@@ -26,7 +26,8 @@ def child(N, M):
     ks, tot = [], []
     for _ in range(7):
         r = e.run(M, 67, m.x, m.k, no_recheck=nr)
-        ks.append(e.last_main_kernel_ms()[0])
+        avg, launches = e.last_main_kernel_ms()   # average per launch; a run is split into chunks
+        ks.append(avg * launches)
         tot.append(r.device_ms)
     raw = e.run(M, 67, m.x, m.k, no_recheck=True)
     kms = float(np.median(ks))
@@ -49,7 +50,12 @@ if __name__ == "__main__":
     ref = None
     for lib in libs:
         env = dict(os.environ, MCR_B200_LIB=str(lib))
-        p = subprocess.run([sys.executable, __file__, "--child", str(N), str(M)], env=env, capture_output=True, text=True)
+        try:
+            p = subprocess.run([sys.executable, __file__, "--child", str(N), str(M)], env=env, capture_output=True, text=True,
+                               timeout=float(os.environ.get("MCR_TUNE_CHILD_TIMEOUT", "120")))
+        except subprocess.TimeoutExpired:
+            print(f"{lib.parent.name:12s} TIMEOUT")
+            continue
         if p.returncode != 0:
             print(f"{lib.parent.name:12s} FAILED: {p.stderr.strip().splitlines()[-1] if p.stderr.strip() else p.returncode}")
             continue
