@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) tc_slab_kernel(const TcSlabPa
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_part_S[2][SLAB_KSPLIT][128], s_part_k1[2][SLAB_KSPLIT][128], s_part_k2[2][SLAB_KSPLIT][128];
     __shared__ float s_part_zmax[2][SLAB_KSPLIT][128];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index through a shuffle: warp-uniform for the compiler, so the MMA warp keeps its descriptors in uniform registers
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     constexpr uint32_t TMEM_COLS = 2 * SLAB_ROWS;   // two accumulator regions of SLAB_ROWS columns: all of TMEM
     constexpr int MMA_WARP = SLAB_GEN_THREADS / 32;
     constexpr int EPI_COLS = SLAB_ROWS / SLAB_KSPLIT;   // accumulator columns per epilogue thread
@@ -80,18 +81,19 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) tc_slab_kernel(const TcSlabPa
             for (int kb = 0; kb < KBN; ++kb) {
                 const uint32_t u = (uint32_t)(n * KBN + kb), slot = u & 1;
                 named_bar_sync(1 + slot, SLAB_THREADS);
-                if (lane == 0) {
+                if (elect_one()) {
                     tc_fence_after();
-                    const uint32_t zhi = smem_u32(smem + slot * SLAB_SLOT_BYTES), zlo = zhi + TILE_M * 128;
-                    const uint32_t bhi = zhi + SLAB_Z_BYTES, blo = bhi + SLAB_ROWS * 128;
+                    // descriptors once per K-block; the 16-column K-steps add 2 (32 bytes >> 4) to the address field
+                    const uint64_t zhi_d = make_desc(smem_u32(smem + slot * SLAB_SLOT_BYTES)), zlo_d = zhi_d + (uint64_t)(TILE_M * 128 / 16);
+                    const uint64_t bhi_d = zhi_d + (uint64_t)(SLAB_Z_BYTES / 16), blo_d = bhi_d + (uint64_t)(SLAB_ROWS * 128 / 16);
                     const uint32_t d_tmem = tmem_base + (uint32_t)(n & 1) * SLAB_ROWS;
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t za = pass == 2 ? zlo : zhi;
-                        const uint32_t ba = pass == 1 ? blo : bhi;
+                        const uint64_t za = pass == 2 ? zlo_d : zhi_d;
+                        const uint64_t ba = pass == 1 ? blo_d : bhi_d;
 #pragma unroll
                         for (int ks = 0; ks < KBLOCK / 16; ++ks)
-                            umma_f16(d_tmem, make_desc(za + ks * 32), make_desc(ba + ks * 32), IDESC, (kb | pass | ks) != 0 ? 1u : 0u);
+                            umma_f16(d_tmem, za + 2 * ks, ba + 2 * ks, IDESC, (kb | pass | ks) != 0 ? 1u : 0u);
                     }
                     umma_commit(&s_empty[slot]);
                     if (kb == KBN - 1) umma_commit(&s_done[n & 1]);

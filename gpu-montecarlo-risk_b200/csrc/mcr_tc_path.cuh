@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
                 tc_fence_before();      // our TMEM reads are ordered before the hand-over
                 if (wg == (int)(u & 3u)) {
                     named_bar_sync(1 + g, 128);   // the K-block is complete and everyone is done with the accumulator
-                    if (lane == 0) {
+                    if (elect_one()) {   // a single thread as far as the compiler is concerned: no ELECT retry loop around each UTCHMMA
                         tc_fence_after();
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass) {

@@ -141,7 +141,10 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
     __shared__ uint32_t s_S[128], s_namb[128], s_amb[128];
     __shared__ uint32_t s_cnt[4], s_sum[4];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role's loop state (ring slot,
+    // shared-memory addresses, UMMA descriptors) in uniform registers; as a plain tid >> 5 the issuing lane spent ~16
+    // instructions per MMA (ELECT + R2UR.BROADCAST x5 + a retry branch) moving them there and was the kernel's critical path
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if (tid == 0) {
         for (int b = 0; b < ZS; ++b) mbar_init(&s_zempty[b], 1);
         for (int b = 0; b < WIDE_RING; ++b) { mbar_init(&s_bfull[b], 1); mbar_init(&s_bempty[b], 1); }
@@ -177,35 +180,36 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
             for (int kb = 0; kb < KBN; ++kb, ++ukb) {
                 const uint32_t slot = ukb % ZS;
                 named_bar_sync(1 + slot, ALL);   // Z K-block complete and visible to the async proxy
-                const uint32_t zhi = smem_u32(s_z + slot * ZSLOT), zlo = zhi + NT * 128;
+                // descriptors once per K-block / per transform block; the 16-column K-steps add 2 (32 bytes >> 4) to the address field
+                const uint64_t zhi_d = make_desc(smem_u32(s_z + slot * ZSLOT)), zlo_d = zhi_d + (uint64_t)(NT * 128 / 16);
                 for (int t = p.lower ? (kb >> 1) : 0; t < NSLAB; ++t, ++blk) {
                     // slabs n_early .. : initialised (and the previous tile's epilogue is done with them)
                     if (kb == 0 && t == n_early) named_bar_sync(WIDE_BAR_ACC, ALL);
                     const uint32_t rs = blk % WIDE_RING;
                     mbar_wait(&s_bfull[rs], (blk / WIDE_RING) & 1u);
-                    if (lane == 0) {
+                    if (elect_one()) {
                         tc_fence_after();
-                        const uint32_t bhi = smem_u32(s_ring + rs * WIDE_BLOCK_BYTES), blo = bhi + 128 * 128;
+                        const uint64_t bhi_d = make_desc(smem_u32(s_ring + rs * WIDE_BLOCK_BYTES)), blo_d = bhi_d + (uint64_t)(128 * 128 / 16);
                         const uint32_t d_tmem = tmem_base + (uint32_t)t * NT;
 #pragma unroll
                         for (int pass = 0; pass < (MCR_WIDE_ABLATE == 3 ? 0 : 3); ++pass) {
-                            const uint32_t ba = pass == 1 ? blo : bhi;   // transform: hi, lo, hi
-                            const uint32_t za = pass == 2 ? zlo : zhi;   // normals:   hi, hi, lo
+                            const uint64_t ba = pass == 1 ? blo_d : bhi_d;   // transform: hi, lo, hi
+                            const uint64_t za = pass == 2 ? zlo_d : zhi_d;   // normals:   hi, hi, lo
 #pragma unroll
                             for (int ks = 0; ks < KBLOCK / 16; ++ks)
-                                umma_f16(d_tmem, make_desc(ba + ks * 32), make_desc(za + ks * 32), IDESC, 1u);
+                                umma_f16(d_tmem, ba + 2 * ks, za + 2 * ks, IDESC, 1u);
                         }
                         umma_commit(&s_bempty[rs]);
                     }
                     __syncwarp();
                 }
-                if (lane == 0) {
+                if (elect_one()) {
                     umma_commit(&s_zempty[slot]);
                     if ((kb & 1) && (kb >> 1) < n_early) umma_commit(&s_slabdone[kb >> 1]);
                 }
                 __syncwarp();
             }
-            if (lane == 0) umma_commit(&s_done);
+            if (elect_one()) umma_commit(&s_done);
             __syncwarp();
         }
     } else if (warp == LOAD_WARP) {
