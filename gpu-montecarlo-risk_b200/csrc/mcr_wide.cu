@@ -40,30 +40,34 @@ constexpr int WIDE_GEN_THREADS = 512;
 constexpr int WIDE_THREADS = WIDE_GEN_THREADS + 64;       // + warp 16: MMA issue, warp 17: transform loader
 // Shared memory is split between Z slots (K-blocks of normals the generators may be ahead of the tensor core) and the ring of
 // transform blocks in flight from L2.  Z slot = NT * 256 B, transform block = 32 KB; ~221 KB usable next to the static part.
-// Measured (profiles/r01_wide_zslots_early_epilogue.log): depth matters little — every combination is within 3 % — because
-// the MMAs are bound by shared-memory operand bandwidth, not by hand-over stalls; the defaults are the fastest combination.
+// Measured (profiles/r01_wide_zslots_early_epilogue.log, r01_mma_issue_fix.log): more than two Z slots buy nothing, so the
+// ring gets the memory.
 #ifndef MCR_WIDE_ZSLOTS_128
-#define MCR_WIDE_ZSLOTS_128 3
+#define MCR_WIDE_ZSLOTS_128 2
 #endif
 #ifndef MCR_WIDE_RING_128
-#define MCR_WIDE_RING_128 3
+#define MCR_WIDE_RING_128 4
 #endif
 #ifndef MCR_WIDE_ZSLOTS_96
-#define MCR_WIDE_ZSLOTS_96 5
+#define MCR_WIDE_ZSLOTS_96 2
 #endif
 #ifndef MCR_WIDE_RING_96
-#define MCR_WIDE_RING_96 3
+#define MCR_WIDE_RING_96 5
 #endif
 #ifndef MCR_WIDE_ZSLOTS_64
-#define MCR_WIDE_ZSLOTS_64 6
+#define MCR_WIDE_ZSLOTS_64 2
 #endif
 #ifndef MCR_WIDE_RING_64
-#define MCR_WIDE_RING_64 3
+#define MCR_WIDE_RING_64 5
 #endif
-// Lower-triangular transform: slab t (last MMAs in K-block 2t + 1) is thresholded and re-initialised inside the K loop, before
-// the generators start K-block 2t + 1 + MCR_WIDE_ELAG; 0 = every slab at the tile boundary.
+// Lower-triangular transform: with MCR_WIDE_ELAG = E > 0 slab t (last MMAs in K-block 2t + 1) is thresholded and re-initialised
+// inside the K loop, before the generators start K-block 2t + 1 + E; 0 = every slab at the tile boundary.  Correct either way
+// (tests run with both), but measured slower with E = 2 / 3 (N = 320: 14.6 / 13.6 ms against 12.7 per 2e7 trials, N = 600:
+// 32.4 / 31.8 against 30.8; before the MMA-issue fix the order was the reverse by 2 %): the ncu capture shows the generators
+// waiting for the slab's MMAs in the middle of the tile (29 % of all warp samples), time they do not lose at the tile boundary,
+// where the tensor core already has two K-blocks of the next tile queued.
 #ifndef MCR_WIDE_ELAG
-#define MCR_WIDE_ELAG 3
+#define MCR_WIDE_ELAG 0
 #endif
 __host__ __device__ constexpr int wide_zslots(int nt) { return nt >= 128 ? MCR_WIDE_ZSLOTS_128 : nt >= 96 ? MCR_WIDE_ZSLOTS_96 : MCR_WIDE_ZSLOTS_64; }
 __host__ __device__ constexpr int wide_ring(int nt) { return nt >= 128 ? MCR_WIDE_RING_128 : nt >= 96 ? MCR_WIDE_RING_96 : MCR_WIDE_RING_64; }

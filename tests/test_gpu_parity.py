@@ -399,10 +399,10 @@ def test_large_n_row_slab_tensor_kernel_bit_exact(engine, oracle, N, mode, M):
 
 @pytest.mark.parametrize("N,mode,tiles", [(320, api.TRANSFORM_LOWER, 3), (600, api.TRANSFORM_LOWER, 3), (300, api.TRANSFORM_GSL_FULL, 2)])
 def test_single_pass_kernel_several_tiles_per_cta(engine, oracle, N, mode, tiles):
-    """The single-pass kernel (257 <= N <= 640) pipelines across the tiles of a CTA: with a lower-triangular transform a slab
-    is thresholded and re-initialised inside the K loop as soon as its last K-block is done, the last slab(s) at the tile
-    boundary while the next tile's first K-blocks are generated.  Enough trials for several tiles per CTA plus a ragged one;
-    per-trial S identical to the oracle."""
+    """The single-pass kernel (257 <= N <= 640) pipelines across the tiles of a CTA: the accumulators of a tile are thresholded
+    and re-initialised (same pass) while the next tile's first K-blocks are already queued for the tensor core - at the tile
+    boundary by default, slab by slab inside the K loop in builds with MCR_WIDE_ELAG > 0.  Enough trials for several tiles per
+    CTA plus a ragged one; per-trial S identical to the oracle."""
     m = synthetic_model(N)
     A = engine.upload_sigma(m.mu, m.Sigma, mode)
     nt = 128 if N <= 512 else 96
