@@ -28,7 +28,8 @@ extern "C" {
                                     + a full dgemv, src/02-C-serial/monte_carlo_serial.c:36-37,72 */
 
 /* ---- kernel selection ------------------------------------------------------------------ */
-#define MCR_KERNEL_AUTO 0   /* FFMA kernel for N < 36, tensor-core kernel above (row slabs of 128 assets beyond N = 128) */
+#define MCR_KERNEL_AUTO 0   /* FFMA kernel for N < 36, tensor-core kernels above: one tile kernel up to N = 128, beyond it the
+                               single-pass kernel (257..640) or row slabs of 256 assets; MCR_LARGE_N=wide|slab overrides */
 #define MCR_KERNEL_FFMA 1   /* fp32 FFMA2 correlate, normals in registers */
 #define MCR_KERNEL_TENSOR 2 /* tcgen05 batched Z*A^T (fp16x3 split, fp32 accumulate in TMEM), normals staged in shared memory */
 #define MCR_KERNEL_EXACT 3  /* fp64, reference summation order (slow; parity / fix-up kernel) */
