@@ -110,14 +110,28 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU legs
+def use_all_host_threads():
+    """The OpenMP runtime reads OMP_NUM_THREADS once, when it is loaded (import torch does that), and torchrun exports
+    OMP_NUM_THREADS=1 to its workers: set the thread count on the live runtime instead, and report what it says."""
+    import ctypes
+    ncores = os.cpu_count() or 1
+    want = int(os.environ.get("MCR_REF_THREADS", ncores))
+    os.environ["OMP_NUM_THREADS"] = str(want)
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(want)
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return want
+
+
 def cpu_reference_leg(model, budget_s=12.0):
     """Time the reference's own C-serial and OpenMP models (oracle/_ref) on this box's cores."""
     import oracle_lib
     if not oracle_lib.ref_models_path().exists():
         return None
     ref = oracle_lib.RefModels()
-    ncores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(ncores))
+    ncores = use_all_host_threads()
     out = {}
     devnull = os.open(os.devnull, os.O_WRONLY)
     saved = os.dup(1), os.dup(2)
@@ -161,8 +175,7 @@ def run_reference_impl(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (reference tree was absent at build time)"}))
         return 0
     ref = oracle_lib.RefModels()
-    ncores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(ncores))
+    ncores = use_all_host_threads()
     devnull = os.open(os.devnull, os.O_WRONLY)
     saved = os.dup(1), os.dup(2)
     per = {}
