@@ -19,7 +19,18 @@ constexpr int A_BYTES = 128 * 128;            // 128 rows x 64 fp16, K-major, 12
 constexpr int MAX_OPS = 4;                    // operand tile pairs to rotate over
 constexpr int THREADS = 32 + 256;             // warp 0 issues; warps 1..8 optionally store to shared memory
 
-template <int N>
+// A operand in TMEM (".ts" form, as cute::SM100_MMA_F16BF16_TS issues it): 128 lanes x 8 columns of packed fp16 pairs per K = 16
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+
+// TS = 1: the A operand (4 K-steps = 32 columns) sits in TMEM behind the accumulators instead of in shared memory
+template <int N, int TS>
 __global__ void __launch_bounds__(THREADS, 1) umma_rate(int iters, int nacc, int nops, int stores, long long* clocks, float* sink) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -49,8 +60,12 @@ __global__ void __launch_bounds__(THREADS, 1) umma_rate(int iters, int nacc, int
                 const uint32_t d = tmem_base + (uint32_t)((it % nacc) * N);
                 const int op = it % nops;
                 const uint64_t a = make_desc(smem_u32(s_a + op * A_BYTES)), b = make_desc(smem_u32(s_b + op * B_BYTES));
+                const uint32_t a_tmem = tmem_base + (uint32_t)(nacc * N + 32 * (TS ? op % ((512 - nacc * N) / 32) : 0));
 #pragma unroll
-                for (int ks = 0; ks < KBLOCK / 16; ++ks) umma_f16(d, a + 2 * ks, b + 2 * ks, IDESC, 1u);
+                for (int ks = 0; ks < KBLOCK / 16; ++ks) {
+                    if (TS) umma_f16_ts(d, a_tmem + 8 * ks, b + 2 * ks, IDESC, 1u);
+                    else umma_f16(d, a + 2 * ks, b + 2 * ks, IDESC, 1u);
+                }
             }
             umma_commit(&s_bar);
         }
@@ -77,20 +92,20 @@ __global__ void __launch_bounds__(THREADS, 1) umma_rate(int iters, int nacc, int
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-template <int N>
+template <int N, int TS>
 void run(int nacc, int nops, int stores) {
-    if (nacc * N > 512) return;
+    if (nacc * N + (TS ? 32 : 0) > 512) return;
     long long* d_clk; float* d_sink;
     cudaMalloc(&d_clk, 8); cudaMalloc(&d_sink, 4);
     const size_t smem = MAX_OPS * (A_BYTES + N * 128) + 32768 + 1024;
-    cudaFuncSetAttribute(umma_rate<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(umma_rate<N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int iters = 20000;   // x 4 K-steps
-    umma_rate<N><<<148, THREADS, smem>>>(iters / 10, nacc, nops, stores, d_clk, d_sink);
-    umma_rate<N><<<148, THREADS, smem>>>(iters, nacc, nops, stores, d_clk, d_sink);
+    umma_rate<N, TS><<<148, THREADS, smem>>>(iters / 10, nacc, nops, stores, d_clk, d_sink);
+    umma_rate<N, TS><<<148, THREADS, smem>>>(iters, nacc, nops, stores, d_clk, d_sink);
     cudaError_t e = cudaDeviceSynchronize();
     long long clk = 0;
     cudaMemcpy(&clk, d_clk, 8, cudaMemcpyDeviceToHost);
-    printf("N=%3d  accumulators %d  operand tiles %d  store warps %s : %7.1f clocks per MMA (nominal %d)%s\n", N, nacc, nops,
+    printf("N=%3d  A in %s  accumulators %d  operand tiles %d  store warps %s : %7.1f clocks per MMA (nominal %d)%s\n", N, TS ? "TMEM" : "smem", nacc, nops,
            stores ? "on " : "off", (double)clk / (4.0 * iters), N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
     cudaFree(d_clk); cudaFree(d_sink);
 }
@@ -99,7 +114,10 @@ template <int N>
 void sweep() {
     for (int stores = 0; stores < 2; ++stores)
         for (int nops : {1, 4})
-            for (int nacc : {1, 2, 4}) run<N>(nacc, nops, stores);
+            for (int nacc : {1, 2, 4}) run<N, 0>(nacc, nops, stores);
+    // A in TMEM (not yet run in round 1): expected at the nominal N / 2
+    for (int stores = 0; stores < 2; ++stores)
+        for (int nacc : {1, 2}) run<N, 1>(nacc, 1, stores);
 }
 
 int main() {
