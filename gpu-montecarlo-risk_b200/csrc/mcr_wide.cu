@@ -36,8 +36,15 @@ namespace mcr {
 #ifndef MCR_WIDE_ABLATE
 #define MCR_WIDE_ABLATE 0
 #endif
-constexpr int WIDE_GEN_THREADS = 512;
-constexpr int WIDE_THREADS = WIDE_GEN_THREADS + 64;       // + warp 16: MMA issue, warp 17: transform loader
+// Generator / epilogue threads per CTA (+ 64: one MMA-issue warp, one transform-loader warp).  PARTS = the largest power of two
+// <= threads / NT of them share a trial's K-block, so with 512 threads a 96-trial tile (513 <= N <= 640) keeps only 384 busy
+// generating; MCR_WIDE_GEN_THREADS_96 = 768 gives it 8 parts of 8 columns (build option, to be measured in round 2; 72 registers
+// per thread then).
+#ifndef MCR_WIDE_GEN_THREADS_96
+#define MCR_WIDE_GEN_THREADS_96 512
+#endif
+__host__ __device__ constexpr int wide_gen_threads(int nt) { return nt == 96 ? MCR_WIDE_GEN_THREADS_96 : 512; }
+__host__ __device__ constexpr int wide_parts(int nt) { return wide_gen_threads(nt) / nt >= 8 ? 8 : 4; }
 // Shared memory is split between Z slots (K-blocks of normals the generators may be ahead of the tensor core) and the ring of
 // transform blocks in flight from L2.  Z slot = NT * 256 B, transform block = 32 KB; ~221 KB usable next to the static part.
 // Measured (profiles/r01_wide_zslots_early_epilogue.log, r01_mma_issue_fix.log): more than two Z slots buy nothing, so the
@@ -123,9 +130,12 @@ __device__ __forceinline__ uint32_t transpose_step(uint32_t x, int lane) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WideParams p) {
+__global__ void __launch_bounds__(wide_gen_threads(NT) + 64, 1) tc_wide_kernel(const WideParams p) {
     using namespace tc;
-    constexpr int PARTS = NT == 64 ? 8 : 4;            // generator threads per trial
+    constexpr int WIDE_GEN_THREADS = wide_gen_threads(NT);
+    constexpr int PARTS = wide_parts(NT);              // generator threads per trial
+    constexpr int QWARPS = WIDE_GEN_THREADS / 128;     // warps per TMEM lane quarter
+    static_assert(PARTS * NT <= WIDE_GEN_THREADS && WIDE_GEN_THREADS % 128 == 0, "generator thread layout");
     constexpr int PCOLS = KBLOCK / PARTS;              // columns per generator thread and K-block
     constexpr uint32_t ZSLOT = 2 * NT * 128;           // one K-block of Z: hi then lo
     constexpr uint32_t IDESC = make_idesc(NT);
@@ -245,13 +255,13 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
         const uint32_t r7s = (uint32_t)(trial % 8) << 4;
         const int quarter = warp & 3;                        // TMEM lanes 32 * quarter .. : rows of a slab
         const uint32_t taddr_q = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const int wq = warp >> 2;                            // which of the quarter's four warps: owns pieces wq, wq + 4, ...
+        const int wq = warp >> 2;                            // which of the quarter's QWARPS warps: owns pieces wq, wq + QWARPS, ...
         uint32_t ukb = 0, done_parity = 0;
 
         // the 32 x 32 pieces (slab t, trial group g) of this quarter's lanes are dealt round-robin to its four warps
         auto init_accumulators = [&]() {
 #pragma unroll 1
-            for (int pc = wq; pc < NSLAB * G32; pc += 4) {
+            for (int pc = wq; pc < NSLAB * G32; pc += QWARPS) {
                 const int t = pc / G32, g = pc - t * G32;
                 const uint32_t c = __float_as_uint(__ldg(p.c_scaled + t * 128 + quarter * 32 + lane));   // (mu_i + x) * 2^10 of this lane's row
                 tmem_st32_bcast(taddr_q + (uint32_t)(t * NT + 32 * g), c);
@@ -283,7 +293,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_wide_kernel(const WidePara
 #pragma unroll
             for (int g = 0; g < G32; ++g) Sloc[g] = 0u;
 #pragma unroll 1
-            for (int pc = wq; pc < (t1 - t0) * G32; pc += 4) {
+            for (int pc = wq; pc < (t1 - t0) * G32; pc += QWARPS) {
                 const int t = t0 + pc / G32, g = pc % G32;
                 const float dr = p.delta_rel[t], da = p.delta_abs[t];
                 const float thr_max = __fmaf_rn(dr, znmax, da);
@@ -491,7 +501,7 @@ static cudaError_t wide_launch_nt(const WideParams& p, int num_sms, cudaStream_t
     if (e != cudaSuccess) return e;
     const uint64_t tiles = (p.M + NT - 1) / NT;
     const int grid = (int)std::min<uint64_t>((uint64_t)num_sms, tiles ? tiles : 1);
-    tc_wide_kernel<NT><<<grid, WIDE_THREADS, smem, s>>>(p);
+    tc_wide_kernel<NT><<<grid, wide_gen_threads(NT) + 64, smem, s>>>(p);
     return cudaGetLastError();
 }
 
