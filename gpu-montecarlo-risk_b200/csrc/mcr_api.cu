@@ -143,6 +143,16 @@ int mcr_build_transform(const double* Sigma, int N, int lds, int mode, double* A
     return 0;
 }
 
+void* mcr_host_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        fail("mcr_host_alloc_pinned: cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+void mcr_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
 // ---- engine --------------------------------------------------------------------------------------
 int mcr_create(int device, mcr_engine** out) {
     if (!out) return fail("mcr_create: null out");
@@ -164,6 +174,7 @@ int mcr_create(int device, mcr_engine** out) {
     ok(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     ok(cudaEventCreate(&e->ev0));
     ok(cudaEventCreate(&e->ev1));
+    ok(cudaEventCreateWithFlags(&e->ev_run_done, cudaEventDisableTiming));
     for (int i = 0; i < 2 * MAX_TIMED_CHUNKS; ++i) ok(cudaEventCreate(&e->evk[i]));
     ok(cudaMalloc(&e->d_flag_list, sizeof(uint32_t) * FLAG_CAP));
     ok(cudaMalloc(&e->d_flag_count, sizeof(uint32_t)));
@@ -198,6 +209,7 @@ int mcr_destroy(mcr_engine* e) {
     if (e->h_partials) cudaFreeHost(e->h_partials);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_run_done) cudaEventDestroy(e->ev_run_done);
     for (int i = 0; i < 2 * MAX_TIMED_CHUNKS; ++i) if (e->evk[i]) cudaEventDestroy(e->evk[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -217,14 +229,10 @@ int mcr_upload_model(mcr_engine* e, int N, const double* mu, const double* A, in
         }
     }
     MCR_CUDA(cudaStreamSynchronize(e->stream));
-    e->N = N;
-    e->lower = a_is_lower != 0;
-    e->mu.assign(mu, mu + N);
-    e->A.assign(A, A + (size_t)N * N);
-    e->w.assign(N, 1.0 / N);
-    e->packed.assign(registry().n, std::vector<float>());
-    e->gen = g_next_gen.fetch_add(1);
-    // fp64 copies for the exact / fix-up kernel (A column-major)
+    if (e->run_pending) { MCR_CUDA(cudaEventSynchronize(e->ev_run_done)); e->run_pending = false; }   // a run on a caller's stream
+    // device copies first (fp64 for the exact / fix-up kernels: A column-major and row-major); the model is published
+    // - N, generation, host copies - only once they are in place, so a failed upload leaves no half-uploaded model behind
+    e->N = 0;
     if (N != e->N_alloc) {
         cudaFree(e->d_mu); cudaFree(e->d_Acm); cudaFree(e->d_Arm);
         e->d_mu = nullptr; e->d_Acm = nullptr; e->d_Arm = nullptr; e->N_alloc = 0;
@@ -239,6 +247,13 @@ int mcr_upload_model(mcr_engine* e, int N, const double* mu, const double* A, in
     MCR_CUDA(cudaMemcpy(e->d_mu, mu, sizeof(double) * N, cudaMemcpyHostToDevice));
     MCR_CUDA(cudaMemcpy(e->d_Acm, Acm.data(), sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice));
     MCR_CUDA(cudaMemcpy(e->d_Arm, A, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice));   // row-major, per-decision fix-up
+    e->lower = a_is_lower != 0;
+    e->mu.assign(mu, mu + N);
+    e->A.assign(A, A + (size_t)N * N);
+    e->w.assign(N, 1.0 / N);
+    e->packed.assign(registry().n, std::vector<float>());
+    e->gen = g_next_gen.fetch_add(1);
+    e->N = N;
     // guard-band ingredient: gamma_i * sum_j |A_ij| with gamma_i = (terms_i + 3) * 2^-24
     const double u = std::ldexp(1.0, -24);
     e->gamma_rowabs_max = 0;
@@ -349,9 +364,16 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
     RunPlan plan;
     if (make_plan(e, opt, dZ != nullptr, &plan)) return -1;
     const int N = e->N;
+    // S >= k with k <= 0 holds for every trial (the reference compares signed ints, serial.c:137-141); the fast kernels compare
+    // unsigned, so clamp once here and every kernel of the run agrees with the reference
+    if (k < 0) k = 0;
+    // One run in flight per engine: every run shares the engine's scratch (fix-up lists, accumulators, block partials,
+    // operand images, the FFMA constant bank).  A run enqueued on another stream waits for the previous one.
+    if (e->run_pending) MCR_CUDA(cudaStreamWaitEvent(s, e->ev_run_done, 0));
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     int32_t* d_S = opt ? opt->d_S_values : nullptr;
     int launches = 0;
+    double mma_flops = 0;   // fp16 MMA flops the tensor pipe executes per trial (0 on the FFMA / fp64 kernels)
     // histogram of S: needs the per-trial S of every chunk; use the caller's buffer or a per-chunk scratch one
     const bool want_hist = opt && opt->want_hist;
     bool S_is_scratch = false;
@@ -438,14 +460,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             e->tc_image_cap = bytes; e->tc_gen = 0;
         }
         std::vector<double> c(N);
-        double cabs_max = 0, rowabs_max = 0;
-        for (int i = 0; i < N; ++i) {
-            c[i] = e->mu[i] + x;
-            cabs_max = std::max(cabs_max, std::fabs(c[i]));
-            double srow = 0;
-            for (int j = 0; j < N; ++j) srow += std::fabs(e->A[(size_t)i * N + j]);
-            rowabs_max = std::max(rowabs_max, srow);
-        }
+        for (int i = 0; i < N; ++i) c[i] = e->mu[i] + x;
         // portfolio row: P = w.R = w.mu + (w^T A) z rides through the same MMAs as one more output row
         std::vector<double> port_row;
         if (plan.portfolio) {
@@ -472,25 +487,36 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         const uint64_t image_key = e->gen * 2 + (plan.portfolio ? 1 : 0);
         if (e->tc_gen != image_key || e->tc_x != x || plan.portfolio) {
             e->tc_host_image.resize(bytes);
-            tc_build(N, rows, e->A.data(), c.data(), plan.portfolio ? port_row.data() : nullptr, e->tc_host_image.data());
+            e->tc_row_scale.assign(tc_padded_n(rows), 1.0);
+            tc_build(N, rows, e->A.data(), c.data(), plan.portfolio ? port_row.data() : nullptr, e->tc_host_image.data(), e->tc_row_scale.data());
             MCR_CUDA(cudaStreamSynchronize(s));   // a previous run may still read the old image
             MCR_CUDA(cudaMemcpyAsync(e->d_tc_image, e->tc_host_image.data(), bytes, cudaMemcpyHostToDevice, s));
             e->tc_gen = image_key; e->tc_x = x;
         }
-        // fp16x3: each operand is hi + lo with relative residual 2^-22 (plus fp16-subnormal rounding of tiny
-        // z_lo, absolute 2^-25 per normal), the lo*lo product is dropped, and the tensor core accumulates in
-        // fp32 over 12*KB MMA instructions: budget 2^-19 relative to |c| + sum_j |a_ij||z_j| (3 * 2^-22 for the
-        // split, the rest for accumulation), doubled like the FFMA band.  Calibration on 4M trials per size:
+        if (plan.portfolio) tl.port_scale = e->tc_row_scale[tc_padded_n(rows) - 1];
+        // Guard band, in accumulator units (accumulator i = s_i (R_i + x), s_i the row's power-of-two scale).  fp16x3: each
+        // operand is hi + lo with relative residual 2^-22 (plus fp16-subnormal rounding of tiny z_lo, absolute 2^-25 per
+        // normal), the lo*lo product is dropped, and the tensor core accumulates in fp32 over 12*KB MMA instructions: budget
+        // 2^-19 relative to |c| + sum_j |a_ij||z_j| (3 * 2^-22 for the split, the rest for accumulation), doubled like the
+        // FFMA band (derivation and the assumed accumulation model: DESIGN.md section 3.1).  Calibration on 4M trials per size:
         // counts are still exact with the band at 1/64 of this (profiles/r01_tc_band_calibrate.log).
         static const double band_scale = [] { const char* v = getenv("MCR_TC_BAND_SCALE"); return v && *v ? atof(v) : 1.0; }();
         const double gamma = std::ldexp(1.0, -19);
-        tl.delta_rel = plan.recheck ? round_up_to_float(band_scale * 2.0 * gamma * rowabs_max) : 0.f;
-        tl.delta_abs = plan.recheck ? round_up_to_float(band_scale * 2.0 * gamma * cabs_max + 1e-30) : 0.f;
+        double cabs_max = 0, rowabs_max = 0;
+        for (int i = 0; i < N; ++i) {
+            double srow = 0;
+            for (int j = 0; j < N; ++j) srow += std::fabs(e->A[(size_t)i * N + j]);
+            rowabs_max = std::max(rowabs_max, srow * e->tc_row_scale[i]);
+            cabs_max = std::max(cabs_max, std::fabs(c[i]) * e->tc_row_scale[i]);
+        }
+        tl.delta_rel = plan.recheck ? band_scale * 2.0 * gamma * rowabs_max : 0.0;
+        tl.delta_abs = plan.recheck ? band_scale * 2.0 * gamma * cabs_max + 1e-30 : 0.0;
         int bps = 0;
         MCR_CUDA(tc_occupancy(plan.rows, plan.portfolio, &bps));
         if (bps < 1) return fail("tensor-core kernel for N=%d%s does not fit one SM's shared memory", N, plan.portfolio ? " with the portfolio histogram" : "");
         if (const char* ov = getenv("MCR_TC_CTAS_PER_SM")) { if (atoi(ov) > 0) bps = atoi(ov); }  // tuning override
         tc_grid_full = std::min(e->num_sms * bps, MAX_GRID);
+        mma_flops = 3.0 * 2.0 * tc_padded_n(rows) * (64.0 * ((rows + 64) / 64)) * 1.0;   // 3 passes over the padded NOUT x K tile (K covers N + 1 columns)
         tl.key0 = key0; tl.key1 = key1; tl.k = k; tl.d_image = e->d_tc_image;
         tl.flag_list = e->d_flag_list; tl.flag_count = e->d_flag_count; tl.flag_cap = FLAG_CAP;
         tl.pair_list = plan.recheck ? e->d_pair_list : nullptr; tl.pair_count = e->d_pair_count; tl.pair_cap = PAIR_CAP;
@@ -514,7 +540,8 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         if (e->slab_gen != e->gen || e->slab_x != x) {
             e->slab_host_image.resize(bytes);
             e->slab_offsets.assign(ns + 1, 0);
-            slab_build(N, e->lower, e->A.data(), c.data(), e->slab_host_image.data(), e->slab_offsets.data());
+            e->slab_row_scale.assign(N, 1.0);
+            slab_build(N, e->lower, e->A.data(), c.data(), e->slab_host_image.data(), e->slab_offsets.data(), e->slab_row_scale.data());
             MCR_CUDA(cudaStreamSynchronize(s));
             MCR_CUDA(cudaMemcpyAsync(e->d_slab_image, e->slab_host_image.data(), bytes, cudaMemcpyHostToDevice, s));
             e->slab_gen = e->gen; e->slab_x = x;
@@ -527,13 +554,14 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             // band at 1/16 of this setting (profiles/r01_tc_band_calibrate_slab_*.log)
             const double gamma = std::ldexp(1.0, -19) * std::max(1.0, kbn / 8.0);
             // sum_j |a_ij||z_j| <= ||a_i||_2 ||z||_2 (Cauchy-Schwarz): the kernel tracks ||z||_2 of the trial
-            double cabs = 0, rownorm = 0;
+            double cabs = 0, rownorm = 0;   // in accumulator units: row i is scaled by slab_row_scale[i]
             for (int i = slab_rows() * t; i < std::min(N, slab_rows() * (t + 1)); ++i) {
-                cabs = std::max(cabs, std::fabs(c[i]));
+                cabs = std::max(cabs, std::fabs(c[i]) * e->slab_row_scale[i]);
                 double ss = 0;
                 for (int j = 0; j < N; ++j) ss += e->A[(size_t)i * N + j] * e->A[(size_t)i * N + j];
-                rownorm = std::max(rownorm, std::sqrt(ss));
+                rownorm = std::max(rownorm, std::sqrt(ss) * e->slab_row_scale[i]);
             }
+            mma_flops += 3.0 * 2.0 * slab_rows() * 64.0 * kbn;
             slab_drel.push_back(plan.recheck ? band_scale * 2.0 * gamma * rownorm : 0.0);
             slab_dabs.push_back(plan.recheck ? band_scale * 2.0 * gamma * cabs + 1e-30 : 0.0);
         }
@@ -555,7 +583,8 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         if (e->wide_gen != e->gen || e->wide_x != x) {
             e->wide_host_image.resize(bytes);
             e->wide_host_c.assign(128 * WIDE_MAX_SLABS, 0.f);
-            wide_build(N, e->lower, e->A.data(), c.data(), e->wide_host_image.data(), e->wide_host_c.data());
+            e->wide_row_scale.assign(N, 1.0);
+            wide_build(N, e->lower, e->A.data(), c.data(), e->wide_host_image.data(), e->wide_host_c.data(), e->wide_row_scale.data());
             MCR_CUDA(cudaStreamSynchronize(s));   // a previous run may still read the old image
             MCR_CUDA(cudaMemcpyAsync(e->d_wide_image, e->wide_host_image.data(), bytes, cudaMemcpyHostToDevice, s));
             MCR_CUDA(cudaMemcpyAsync(e->d_wide_c, e->wide_host_c.data(), sizeof(float) * 128 * ns, cudaMemcpyHostToDevice, s));
@@ -571,12 +600,13 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             for (int i = 128 * t; i < std::min(N, 128 * (t + 1)); ++i) {
                 double ss = 0;
                 for (int j = 0; j < N; ++j) ss += e->A[(size_t)i * N + j] * e->A[(size_t)i * N + j];
-                rownorm = std::max(rownorm, std::sqrt(ss));
-                cabs = std::max(cabs, std::fabs(c[i]));
+                rownorm = std::max(rownorm, std::sqrt(ss) * e->wide_row_scale[i]);
+                cabs = std::max(cabs, std::fabs(c[i]) * e->wide_row_scale[i]);
             }
             wl.delta_rel[t] = plan.recheck ? band_scale * 2.0 * gamma * rownorm : 0.0;
             wl.delta_abs[t] = plan.recheck ? band_scale * 2.0 * gamma * cabs + 1e-30 : 0.0;
         }
+        mma_flops = 3.0 * 2.0 * 128.0 * 64.0 * (double)(bytes / (2 * 128 * 128));   // per transform block: 128 rows x 64 columns, 3 passes
         wl.key0 = key0; wl.key1 = key1; wl.N = N; wl.k = k; wl.lower = e->lower ? 1 : 0;
         wl.d_image = e->d_wide_image; wl.d_c_scaled = e->d_wide_c;
         wl.flag_list = e->d_flag_list; wl.flag_count = e->d_flag_count; wl.flag_cap = FLAG_CAP;
@@ -714,6 +744,9 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         }
     }
     e->last_kernel = plan.kernel; e->last_NT = plan.NT; e->last_launches = launches; e->last_portfolio = plan.portfolio;
+    e->last_mma_flops = mma_flops;
+    MCR_CUDA(cudaEventRecord(e->ev_run_done, s));
+    e->run_pending = true;
     return 0;
 }
 
@@ -766,6 +799,12 @@ int mcr_last_main_kernel_ms(mcr_engine* e, float* avg_ms, int* n_launches) {
     }
     *n_launches = e->n_timed;
     *avg_ms = e->n_timed ? (float)(sum / e->n_timed) : 0.f;
+    return 0;
+}
+
+int mcr_last_mma_flops_per_trial(mcr_engine* e, double* flops) {
+    if (!e || !flops) return fail("mcr_last_mma_flops_per_trial: null argument");
+    *flops = e->last_mma_flops;
     return 0;
 }
 

@@ -27,6 +27,8 @@ struct mcr_engine {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_run_done = nullptr;   // recorded at the end of every enqueued run: the next run (any stream) waits for it
+    bool run_pending = false;
     cudaEvent_t evk[2 * mcr::MAX_TIMED_CHUNKS] = {};  // (start, stop) around each path-kernel launch of the last run
     int n_timed = 0;
     // model
@@ -44,6 +46,7 @@ struct mcr_engine {
     uint64_t tc_gen = 0;
     double tc_x = 0;
     std::vector<uint8_t> tc_host_image;
+    std::vector<double> tc_row_scale;     // power-of-two scale of every accumulator row of the current image
     // row-slab tensor path (N > 128)
     void* d_slab_image = nullptr;
     size_t slab_image_cap = 0;
@@ -51,6 +54,7 @@ struct mcr_engine {
     double slab_x = 0;
     std::vector<uint8_t> slab_host_image;
     std::vector<size_t> slab_offsets;
+    std::vector<double> slab_row_scale;
     uint16_t* d_S_acc = nullptr;
     // single-pass wide tensor path (128 < N <= 1024)
     void* d_wide_image = nullptr;
@@ -60,6 +64,7 @@ struct mcr_engine {
     double wide_x = 0;
     std::vector<uint8_t> wide_host_image;
     std::vector<float> wide_host_c;
+    std::vector<double> wide_row_scale;
     unsigned long long* d_pair_list = nullptr;   // single near-threshold (trial, row) decisions of a chunk
     uint32_t* d_pair_count = nullptr;
     double* d_Arm = nullptr;                     // fp64 transform, row-major (per-decision fix-up)
@@ -89,6 +94,7 @@ struct mcr_engine {
     std::vector<double> h_ext_sums;
     // last async run bookkeeping
     int last_kernel = 0, last_NT = 0, last_launches = 0;
+    double last_mma_flops = 0;   // fp16 MMA flops per trial the tensor pipe executed in the last run
 };
 
 namespace mcr {

@@ -110,7 +110,7 @@ struct TcLaunch {
     uint64_t M, path_offset;
     uint32_t key0, key1;
     int32_t k;
-    float delta_rel, delta_abs;  // guard band = delta_rel * max_j|z_j| + delta_abs
+    double delta_rel, delta_abs; // guard band = delta_rel * max_j|z_j| + delta_abs, in accumulator units (row scales applied)
     const void* d_image;        // device copy of the split, swizzled transform image (tc_build)
     int32_t* S_out;
     uint32_t* flag_list;
@@ -123,6 +123,7 @@ struct TcLaunch {
     // portfolio extension
     int32_t portfolio;
     double port_x, hist_lo, hist_width;
+    double port_scale;          // power-of-two scale of the portfolio row (tc_build's row_scale[rows - 1])
     double* port_acc;
     unsigned long long* port_hist;
     double* port_hist_sum;
@@ -134,7 +135,9 @@ size_t tc_image_bytes(int rows);
 int tc_padded_n(int rows);
 // A: N x N row-major fp64 transform, c: N thresholds mu_i + x, port_row: nullptr or N + 1 values
 // (w^T A, then w.mu)  ->  host image (tc_image_bytes(rows))
-void tc_build(int N, int rows, const double* A, const double* c, const double* port_row, uint8_t* image);
+// row_scale: out, tc_padded_n(rows) entries = the power-of-two scale of every accumulator row (tc_row_scale)
+void tc_build(int N, int rows, const double* A, const double* c, const double* port_row, uint8_t* image, double* row_scale);
+double tc_z_factor();   // what tc_build multiplies the transform columns by (the generator's folded sqrt(2 ln 2), or 1)
 cudaError_t tc_occupancy(int rows, bool portfolio, int* blocks_per_sm);
 cudaError_t tc_launch(int N, int rows, const TcLaunch& l, int grid, cudaStream_t s);
 
@@ -143,7 +146,7 @@ struct SlabLaunch {
     uint64_t M, path_offset;
     uint32_t key0, key1;
     int32_t ncols;               // normal columns this slab multiplies
-    double delta_rel, delta_abs; // unscaled guard band of this slab
+    double delta_rel, delta_abs; // guard band of this slab in accumulator units (row scales applied)
     const void* d_slab_image;    // device image of this slab (slab_build)
     uint16_t* S_acc;             // [M] running per-trial hit count, bit 15 = flagged
     int32_t first_slab;
@@ -156,7 +159,7 @@ int slab_rows();
 int slab_count(int N);
 int slab_ncols(int N, int t, bool lower);
 size_t slab_image_bytes(int N, bool lower);
-void slab_build(int N, bool lower, const double* A, const double* c, uint8_t* image, size_t* offsets);
+void slab_build(int N, bool lower, const double* A, const double* c, uint8_t* image, size_t* offsets, double* row_scale /* N, out */);
 cudaError_t slab_launch(const SlabLaunch& l, int num_sms, cudaStream_t s);
 cudaError_t slab_count_launch(uint64_t M, const uint16_t* S_acc, int k, int32_t* S_out, uint32_t* flag_list,
                               uint32_t* flag_count, uint32_t flag_cap, uint64_t* block_partials, int grid, cudaStream_t s);
@@ -169,7 +172,7 @@ struct WideLaunch {
     int32_t N, k, lower;
     const void* d_image;         // wide_build image on the device
     const float* d_c_scaled;     // wide_build thresholds on the device
-    double delta_rel[WIDE_MAX_SLABS], delta_abs[WIDE_MAX_SLABS];   // unscaled guard band per 128-row slab (relative to ||z||_2)
+    double delta_rel[WIDE_MAX_SLABS], delta_abs[WIDE_MAX_SLABS];   // guard band per 128-row slab (relative to ||z||_2), accumulator units
     int32_t* S_out;
     uint32_t* flag_list;
     uint32_t* flag_count;
@@ -184,7 +187,7 @@ int wide_slabs(int N);
 int wide_kblocks(int N);
 int wide_trials_per_tile(int N);
 size_t wide_image_bytes(int N, bool lower);
-void wide_build(int N, bool lower, const double* A, const double* c, uint8_t* image, float* c_scaled);
+void wide_build(int N, bool lower, const double* A, const double* c, uint8_t* image, float* c_scaled, double* row_scale /* N, out */);
 int wide_grid(uint64_t M, int N, int num_sms);
 cudaError_t wide_launch(const WideLaunch& l, int num_sms, cudaStream_t s);
 

@@ -297,7 +297,10 @@ size_t tc_image_bytes(int rows) { const TcVariant* v = tc_find(rows); return v ?
 
 int tc_padded_n(int rows) { const TcVariant* v = tc_find(rows); return v ? v->nout : 0; }
 
-void tc_build(int N, int rows, const double* A, const double* c, const double* port_row, uint8_t* image) { tc_find(rows)->build(A, c, N, port_row, image); }
+void tc_build(int N, int rows, const double* A, const double* c, const double* port_row, uint8_t* image, double* row_scale) {
+    tc_find(rows)->build(A, c, N, port_row, image, row_scale);
+}
+double tc_z_factor() { return TC_Z_FACTOR; }
 
 cudaError_t tc_occupancy(int rows, bool portfolio, int* bps) { return tc_find(rows)->occupancy(bps, portfolio); }
 
@@ -305,12 +308,12 @@ cudaError_t tc_launch(int N, int rows, const TcLaunch& l, int grid, cudaStream_t
     TcParams p{};
     p.M = l.M; p.path_offset = l.path_offset; p.key0 = l.key0; p.key1 = l.key1; p.k = l.k; p.N = N;
     p.keys.set(l.key0, l.key1);
-    // accumulators are scaled; with MCR_TC_FOLD the kernel's bound on |z| is in units of sqrt(2 ln 2)
-    p.delta_rel = (float)(l.delta_rel * TC_SCALE * TC_Z_FACTOR * (TC_FOLD ? 1.0 + 1e-6 : 1.0)); p.delta_abs = (float)(l.delta_abs * TC_SCALE);
+    // the band arrives in accumulator units (row scales applied); with MCR_TC_FOLD the kernel's bound on |z| is in units of sqrt(2 ln 2)
+    p.delta_rel = (float)(l.delta_rel * TC_Z_FACTOR * (TC_FOLD ? 1.0 + 1e-6 : 1.0)); p.delta_abs = (float)l.delta_abs;
     p.B_image = reinterpret_cast<const uint4*>(l.d_image); p.S_out = l.S_out;
     p.flag_list = l.flag_list; p.flag_count = l.flag_count; p.flag_cap = l.flag_cap; p.block_partials = l.block_partials;
     p.pair_list = l.pair_list; p.pair_count = l.pair_count; p.pair_cap = l.pair_cap;
-    p.portfolio = l.portfolio; p.port_thresh = (float)(-l.port_x * TC_SCALE);
+    p.portfolio = l.portfolio; p.port_thresh = (float)(-l.port_x * l.port_scale); p.port_inv_scale = (float)(1.0 / l.port_scale);
     p.hist_lo = (float)l.hist_lo; p.hist_inv_w = (float)(1.0 / l.hist_width);
     p.port_acc = l.port_acc; p.port_hist = l.port_hist; p.port_hist_sum = l.port_hist_sum;
     for (int q = 0; q < 8; ++q) {
@@ -334,7 +337,12 @@ size_t slab_image_bytes(int N, bool lower) {
 }
 
 // image of every slab, back to back; offsets[t] = byte offset of slab t (offsets has slab_count(N) + 1 entries)
-void slab_build(int N, bool lower, const double* A, const double* c, uint8_t* image, size_t* offsets) {
+void slab_build(int N, bool lower, const double* A, const double* c, uint8_t* image, size_t* offsets, double* row_scale) {
+    for (int i = 0; i < N; ++i) {
+        double mx = std::fabs(c[i]);
+        for (int k = 0; k < N; ++k) mx = std::max(mx, std::fabs(A[(size_t)i * N + k]));
+        row_scale[i] = tc_row_scale(mx);
+    }
     size_t off = 0;
     for (int t = 0; t < slab_count(N); ++t) {
         offsets[t] = off;
@@ -346,8 +354,8 @@ void slab_build(int N, bool lower, const double* A, const double* c, uint8_t* im
             for (int k = 0; k <= ncols; ++k) {
                 double v;
                 if (k < ncols) v = (i < N) ? A[(size_t)i * N + k] : 0.0;
-                else v = (i < N) ? c[i] : 1.0;
-                v *= TC_SCALE;
+                else v = (i < N) ? c[i] : TC_PAD_ROW;
+                if (i < N) v *= row_scale[i];
                 const __half hi = __float2half_rn((float)v);
                 const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
                 // K-block kb = k / 64: [hi: 128 rows x 128 B][lo: ...], same swizzle as the device-side Z rows
@@ -370,7 +378,7 @@ cudaError_t slab_launch(const SlabLaunch& l, int num_sms, cudaStream_t s) {
     TcSlabParams p{};
     p.M = l.M; p.path_offset = l.path_offset; p.key0 = l.key0; p.key1 = l.key1;
     p.ncols = l.ncols; p.kb_count = slab_kblocks(l.ncols);
-    p.delta_rel = (float)(l.delta_rel * TC_SCALE); p.delta_abs = (float)(l.delta_abs * TC_SCALE);
+    p.delta_rel = (float)l.delta_rel; p.delta_abs = (float)l.delta_abs;   // already in accumulator units
     p.thr_max = p.delta_rel * 7.0f * sqrtf((float)l.ncols) * 1.001f + p.delta_abs;
     p.B_slab = reinterpret_cast<const uint4*>(l.d_slab_image); p.S_acc = l.S_acc; p.first_slab = l.first_slab;
     p.row_base = l.row_base; p.pair_list = l.pair_list; p.pair_count = l.pair_count; p.pair_cap = l.pair_cap;

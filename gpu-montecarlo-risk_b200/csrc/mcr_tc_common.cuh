@@ -2,6 +2,7 @@
 // (mcr_tc.cu: N <= 128 and the row-slab kernel; mcr_wide.cu: the single-pass kernel for N > 128).
 #pragma once
 #include <cstdint>
+#include <cmath>
 #include <cuda_fp16.h>
 
 namespace mcr {
@@ -117,7 +118,19 @@ __host__ __device__ inline uint32_t operand_offset(int rows, int r, int k) {
 
 }  // namespace tc
 
-constexpr double TC_SCALE = 1024.0;  // 2^10, see tc_build_image
+// Scale of one transform row in the fp16 hi + lo operand images: a power of two (so it is exact and signs, the guard band
+// and the portfolio row simply carry it) that puts the row's largest |entry| - its transform entries times the generator's
+// z factor, and its constant mu_i + x - into [2^12, 2^13).  A fixed scale (round 1: 2^10) overflows fp16 for returns
+// expressed in basis points and pushes the lo parts of small-volatility rows into fp16 subnormals, whose 2^-25 absolute
+// rounding error the relative guard band does not cover; per row, every row is as well conditioned as fp16 allows whatever
+// the units of Sigma.  Accumulator i then holds s_i * (R_i + x).
+inline double tc_row_scale(double row_maxabs) {
+    if (!(row_maxabs > 0.0)) return 1.0;
+    int e = 0;
+    (void)frexp(row_maxabs, &e);          // row_maxabs = m * 2^e, m in [0.5, 1)
+    return ldexp(1.0, 13 - e);
+}
+constexpr double TC_PAD_ROW = 4096.0;     // scaled constant of a padded row: far on the "no crash" side
 
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }

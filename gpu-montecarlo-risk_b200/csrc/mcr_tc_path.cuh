@@ -56,7 +56,8 @@ struct TcParams {
     uint64_t* block_partials;
     // portfolio extension (north-star A7; no reference code): accumulator column NOUT-1 holds w.R
     int32_t portfolio;            // 0 = off (column NOUT-1 is an ordinary padded / asset row)
-    float port_thresh;            // scaled: tail event is  D < port_thresh  (= -x_p * TC_SCALE)
+    float port_thresh;            // scaled: tail event is  D < port_thresh  (= -x_p * scale of the portfolio row)
+    float port_inv_scale;         // 1 / scale of the portfolio row
     float hist_lo, hist_inv_w;    // unscaled histogram origin and 1 / bin width
     double* port_acc;             // [4] += hits, sum P, sum P^2, sum of -P over tail events
     unsigned long long* port_hist;  // [MCR_PORTFOLIO_BINS] counts
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
                         } else if (i < p.M) {
                             // portfolio return of this trial (the host put w^T A and w.mu in row NOUT-1)
                             const float Ps = __uint_as_float(v[c]);
-                            const float P = Ps * (float)(1.0 / TC_SCALE);
+                            const float P = Ps * p.port_inv_scale;
                             const bool tail = Ps < p.port_thresh;
                             p_hits += tail ? 1u : 0u;
                             p_tail += tail ? -P : 0.0f;
@@ -393,21 +394,30 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-// Transform image: rows i < N hold A_ij * 2^10 (columns j < N) and (mu_i + x) * 2^10 (column N); padded
-// rows hold +2^10 in column N so they are always far on the "no crash" side.  Everything is split into
-// fp16 hi + lo.  The 2^10 scale only moves the values (|A| ~ 1e-2, lo parts ~ 1e-6) out of fp16's
-// subnormal range; signs and the (equally scaled) guard band are unaffected.
+// Transform image: row i < N holds s_i * A_ij (columns j < N) and s_i * (mu_i + x) (column N), s_i = the row's power-of-two
+// scale (tc_row_scale; returned in row_scale[NOUT]); padded rows hold a large positive constant in column N so they are
+// always far on the "no crash" side.  Everything is split into fp16 hi + lo.  The scale only moves the values into the
+// middle of fp16's normal range; signs and the (equally scaled) guard band are unaffected.
 template <int NOUT, int KB>
-static void tc_build_image(const double* A, const double* c, int N, const double* port_row, uint8_t* image) {
+static void tc_build_image(const double* A, const double* c, int N, const double* port_row, uint8_t* image, double* row_scale) {
     const size_t bytes = (size_t)KB * NOUT * 128;
     memset(image, 0, 2 * bytes);
+    for (int i = 0; i < NOUT; ++i) {
+        const bool port = port_row && i == NOUT - 1;
+        double mx = 0.0;
+        for (int k = 0; k <= N; ++k) {
+            const double v = port ? port_row[k] : (i < N ? (k < N ? A[(size_t)i * N + k] : c[i]) : 0.0);
+            mx = std::max(mx, std::fabs(v) * (k < N ? TC_Z_FACTOR : 1.0));
+        }
+        row_scale[i] = (port || i < N) ? tc_row_scale(mx) : 1.0;
+    }
     for (int i = 0; i < NOUT; ++i)
         for (int k = 0; k <= N; ++k) {
             double v;
             if (port_row && i == NOUT - 1) v = port_row[k];   // portfolio: w^T A (k < N) and w.mu (k = N)
             else if (k < N) v = (i < N) ? A[(size_t)i * N + k] : 0.0;
-            else v = (i < N) ? c[i] : 1.0;
-            v *= TC_SCALE * (k < N ? TC_Z_FACTOR : 1.0);
+            else v = (i < N) ? c[i] : TC_PAD_ROW;
+            v *= row_scale[i] * (k < N ? TC_Z_FACTOR : 1.0);
             const __half hi = __float2half_rn((float)v);
             const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
             const uint32_t off = tc::operand_offset(NOUT, i, k);
@@ -472,7 +482,7 @@ static cudaError_t tc_occupancy_impl(int* bps, bool portfolio) {
 struct TcVariant {
     int nout, kb, groups;
     size_t image_bytes;
-    void (*build)(const double*, const double*, int, const double*, uint8_t*);
+    void (*build)(const double*, const double*, int, const double*, uint8_t*, double*);
     cudaError_t (*launch)(const TcParams&, int, cudaStream_t);
     cudaError_t (*occupancy)(int*, bool);
 };

@@ -469,10 +469,15 @@ static int wide_blocks(int N, bool lower) {
 
 size_t wide_image_bytes(int N, bool lower) { return (size_t)wide_blocks(N, lower) * WIDE_BLOCK_BYTES; }
 
-// image: transform blocks (kb outer, t inner), each [hi 16 KB | lo 16 KB] of 128 rows x 64 columns of A * 2^10 in the
+// image: transform blocks (kb outer, t inner), each [hi 16 KB | lo 16 KB] of 128 rows x 64 columns of s_i * A_ij (row scales: tc_row_scale) in the
 // K-major 128-byte-swizzled operand layout;  c_scaled: nslab * 128 floats
-void wide_build(int N, bool lower, const double* A, const double* c, uint8_t* image, float* c_scaled) {
+void wide_build(int N, bool lower, const double* A, const double* c, uint8_t* image, float* c_scaled, double* row_scale) {
     const int ns = wide_slabs(N), kbn = wide_kblocks(N);
+    for (int i = 0; i < N; ++i) {
+        double mx = std::fabs(c[i]);
+        for (int k = 0; k < N; ++k) mx = std::max(mx, std::fabs(A[(size_t)i * N + k]));
+        row_scale[i] = tc_row_scale(mx);
+    }
     memset(image, 0, wide_image_bytes(N, lower));
     uint8_t* blk = image;
     for (int kb = 0; kb < kbn; ++kb)
@@ -483,7 +488,7 @@ void wide_build(int N, bool lower, const double* A, const double* c, uint8_t* im
                 for (int kk = 0; kk < tc::KBLOCK; ++kk) {
                     const int j = tc::KBLOCK * kb + kk;
                     if (j >= N) break;
-                    const double v = A[(size_t)i * N + j] * TC_SCALE;
+                    const double v = A[(size_t)i * N + j] * row_scale[i];
                     const __half hi = __float2half_rn((float)v);
                     const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
                     const uint32_t off = tc::operand_offset(128, r, kk);
@@ -491,7 +496,7 @@ void wide_build(int N, bool lower, const double* A, const double* c, uint8_t* im
                     memcpy(blk + 128 * 128 + off, &lo, 2);
                 }
             }
-    for (int i = 0; i < ns * 128; ++i) c_scaled[i] = (float)((i < N ? c[i] : 1.0) * TC_SCALE);
+    for (int i = 0; i < ns * 128; ++i) c_scaled[i] = (float)(i < N ? c[i] * row_scale[i] : TC_PAD_ROW);
 }
 
 template <int NT>
@@ -517,8 +522,8 @@ cudaError_t wide_launch(const WideLaunch& l, int num_sms, cudaStream_t s) {
     p.N = l.N; p.k = l.k; p.kbn = wide_kblocks(l.N); p.nslab = wide_slabs(l.N); p.lower = l.lower;
     p.image = reinterpret_cast<const uint8_t*>(l.d_image); p.c_scaled = l.d_c_scaled;
     for (int t = 0; t < p.nslab; ++t) {
-        p.delta_rel[t] = (float)(l.delta_rel[t] * TC_SCALE);
-        p.delta_abs[t] = (float)(l.delta_abs[t] * TC_SCALE);
+        p.delta_rel[t] = (float)l.delta_rel[t];   // already in accumulator units (row scales applied)
+        p.delta_abs[t] = (float)l.delta_abs[t];
     }
     p.S_out = l.S_out; p.flag_list = l.flag_list; p.flag_count = l.flag_count; p.flag_cap = l.flag_cap;
     p.pair_list = l.pair_list; p.pair_count = l.pair_count; p.pair_cap = l.pair_cap; p.block_partials = l.block_partials;

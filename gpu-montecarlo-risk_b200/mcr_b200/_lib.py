@@ -85,6 +85,8 @@ PROTOTYPES = {
     "mcr_last_error": (C.c_char_p, []),
     "mcr_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "mcr_build_transform": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mcr_host_alloc_pinned": (C.c_void_p, [C.c_size_t]),
+    "mcr_host_free_pinned": (None, [C.c_void_p]),
     "mcr_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "mcr_destroy": (C.c_int, [C.c_void_p]),
     "mcr_upload_model": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
@@ -98,6 +100,7 @@ PROTOTYPES = {
     "mcr_portfolio_hist_range": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mcr_result_from_partials_ext": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.POINTER(Result)]),
     "mcr_last_main_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "mcr_last_mma_flops_per_trial": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "mcr_result_from_partials": (C.c_int, [C.c_void_p, C.POINTER(Result)]),
     "mcr_run_with_normals": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_int,
                                        C.POINTER(RunOptions), C.c_void_p, C.POINTER(Result)]),

@@ -185,6 +185,12 @@ class Engine:
         check(self._lib.mcr_last_main_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def mma_flops_per_trial(self) -> float:
+        """fp16 MMA flops per trial executed by the tensor pipe in the last run (0 for the FFMA / fp64 kernels)."""
+        f = C.c_double(0)
+        check(self._lib.mcr_last_mma_flops_per_trial(self._h, C.byref(f)))
+        return f.value
+
     def measure_fp32_peak(self, ms_target=20.0) -> float:
         t = C.c_double(0)
         check(self._lib.mcr_measure_fp32_peak(self._h, float(ms_target), C.byref(t)))

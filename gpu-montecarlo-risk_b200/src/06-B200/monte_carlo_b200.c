@@ -8,7 +8,8 @@
  * NULL (make_clean is NULL-safe).
  *
  * Differences from the reference CUDA model, by design:
- *   - no N <= 64 cap (cuda.cu:78-81): the FFMA path covers N <= 128, larger N use the fp64 GPU kernel;
+ *   - no N <= 64 cap (cuda.cu:78-81): FFMA2 kernel for small N, tcgen05 tensor-core kernels above (one tile kernel up to
+ *     N = 128, the streamed multi-pass kernels up to N = 1024), every near-threshold decision rechecked in fp64;
  *   - S_values (M ints, written by every reference model but read by nobody) is only produced when
  *     MCR_S_VALUES=1, which saves a 4*M-byte device buffer and D2H copy;
  *   - the transform convention is selectable (MCR_TRANSFORM=lower|gsl_full, see cholesky_upload.h);

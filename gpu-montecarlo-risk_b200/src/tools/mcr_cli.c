@@ -31,8 +31,11 @@ int main(int argc, char **argv) {
     char mu_path[4096], sigma_path[4096];
     snprintf(mu_path, sizeof mu_path, "%s/mu.bin", dir);
     snprintf(sigma_path, sizeof sigma_path, "%s/sigma.bin", dir);
+    /* the payload is staged in pinned host memory (cudaHostAlloc behind the C ABI); header, length and dimension checks come
+     * first, so a bad file is rejected before any allocation (and without a GPU) */
     McrHostModel m;
-    if (mcr_load_host_model(mu_path, sigma_path, &m) != 0) return 1;
+    const McrHostAllocator pinned = {mcr_host_alloc_pinned, mcr_host_free_pinned};
+    if (mcr_load_host_model_ex(mu_path, sigma_path, &pinned, &m) != 0) return 1;
 
     double *A = (double *)malloc((size_t)m.N * m.N * sizeof(double));
     if (!A || mcr_build_transform(m.Sigma, m.N, m.N, mode, A) != 0) {

@@ -14,6 +14,7 @@
 #ifndef MCR_B200_H
 #define MCR_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -91,6 +92,12 @@ int mcr_device_count(int *n_devices);   /* -1 (not 0 devices) when no CUDA drive
  * mode = MCR_TRANSFORM_*.  Fails (-1) when Sigma is not positive definite. */
 int mcr_build_transform(const double *Sigma, int N, int lds, int mode, double *A_out);
 
+/* Pinned (page-locked) host staging for the loader that replaces src/utilities/load_binary.c:13-36,56-87 and for S_values
+ * buffers: uploads and the streamed S_values read-back then run at full PCIe / C2C rate without a bounce copy.
+ * NULL when no CUDA device is usable or the allocation fails. */
+void *mcr_host_alloc_pinned(size_t bytes);
+void mcr_host_free_pinned(void *p);
+
 /* ---- engine life cycle ------------------------------------------------------------------ */
 int mcr_create(int device, mcr_engine **out);
 int mcr_destroy(mcr_engine *e);
@@ -119,6 +126,10 @@ int mcr_run_async(mcr_engine *e, uint64_t M, uint64_t path_offset, uint64_t seed
 /* Device time of the dominant (path) kernel of the engine's most recent run: average CUDA-event duration per
  * launch, and the number of launches timed.  Waits for that run to finish. */
 int mcr_last_main_kernel_ms(mcr_engine *e, float *avg_ms_per_launch, int *n_launches);
+/* fp16 MMA flops per trial the tensor pipe executed in the engine's most recent run (3 passes of the fp16 hi/lo split over
+ * the padded tiles actually issued; 0 for the FFMA and fp64 kernels): the "executed" figure next to the algorithmic
+ * F(N) = N^2 + 3N of the roofline in bench.py. */
+int mcr_last_mma_flops_per_trial(mcr_engine *e, double *flops);
 /* Turn (possibly all-reduced) partial words copied to the host into a result with the reference's statistics. */
 int mcr_result_from_partials(const uint64_t *h_partials, mcr_result *out);
 

@@ -82,12 +82,17 @@ int mcr_oracle_transform(const double *sigma, int N, int mode, double *A) {
         }
         double ajj = A[j * N + j];
         if (!(ajj > 0.0)) return -1;
-        const double inv = 1.0 / sqrt(ajj);
+        /* GSL 2.7 cholesky_decomp_L2 ends the column with gsl_vector_scale(A(j:n,j), 1/sqrt(ajj)), diagonal included
+         * [recalled; GSL is not installed here], so L_jj = ajj * (1/sqrt(ajj)).  MCR_ORACLE_TRANSFORM_DIAG_SQRT stores
+         * L_jj = sqrt(ajj) instead (at most one ulp away); tests/test_oracle_golden.py shows the frozen counts do not
+         * depend on which of the two a GSL build uses. */
+        const double root = sqrt(ajj), inv = 1.0 / root;
         for (int i = j; i < N; i++) A[i * N + j] *= inv;
+        if (mode & MCR_ORACLE_TRANSFORM_DIAG_SQRT) A[j * N + j] = root;
     }
     for (int i = 0; i < N; i++)
         for (int j = i + 1; j < N; j++)
-            A[i * N + j] = (mode == MCR_ORACLE_TRANSFORM_GSL_FULL) ? sigma[j * N + i] : 0.0;
+            A[i * N + j] = ((mode & 1) == MCR_ORACLE_TRANSFORM_GSL_FULL) ? sigma[j * N + i] : 0.0;
     return 0;
 }
 

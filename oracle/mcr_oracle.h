@@ -27,6 +27,7 @@ extern "C" {
 /* transform-matrix conventions */
 #define MCR_ORACLE_TRANSFORM_LOWER 0    /* A = tril(L)            : reference CUDA model, monte_carlos_cuda.cu:100-107 */
 #define MCR_ORACLE_TRANSFORM_GSL_FULL 1 /* A = L + striu(Sigma)   : C-serial/OpenMP after gsl_linalg_cholesky_decomp1 + full dgemv */
+#define MCR_ORACLE_TRANSFORM_DIAG_SQRT 2 /* OR-ed in: L_jj = sqrt(a_jj) instead of a_jj * (1 / sqrt(a_jj)) (one-ulp ambiguity of the recalled GSL code) */
 
 /* Sigma (N x N row-major, fp64) -> A (N x N row-major).  Returns 0, or -1 if not SPD. */
 int mcr_oracle_transform(const double *sigma, int N, int mode, double *A_out);

@@ -11,6 +11,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 ORACLE_DIR = ROOT / "oracle"
 LOWER, GSL_FULL = 0, 1
+DIAG_SQRT = 2   # OR-ed into the mode: L_jj = sqrt(a_jj) (see mcr_oracle.c)
 
 
 def _p(a):
@@ -169,3 +170,18 @@ class RefModels:
 
     def openmp(self, *a, **kw):
         return run_model_struct(self.lib.get_openmp_model, *a, **kw)
+
+
+def ref_cuda_path():
+    return ORACLE_DIR / "_ref" / "libref_cuda.so"
+
+
+class RefCuda:
+    """get_cuda_model of the reference (src/05-GPU/monte_carlos_cuda.cu), compiled UNMODIFIED for sm_100a against the GSL
+    shim (oracle/Makefile): the GPU baseline.  N <= 64 only (monte_carlos_cuda.cu:78-81); always fills S_values."""
+
+    def __init__(self):
+        self.lib = C.CDLL(str(ref_cuda_path()))
+
+    def cuda(self, *a, **kw):
+        return run_model_struct(self.lib.get_cuda_model, *a, **kw)

@@ -1,0 +1,169 @@
+"""GPU parity tests added in round 2 (run on a B200 with -m gpu; everything goes through the C ABI).
+
+  * fast kernels against the fp64 kernel at FULL BASELINE sizes (no oracle can follow there: the fp64 GPU kernel evaluates
+    the reference's summation order on the same Philox normals, and is itself pinned to the oracle at small sizes);
+  * models in other units (Sigma x 1e4 = basis points, Sigma x 1e-6): the per-row power-of-two scale of the fp16 operand
+    images keeps every tensor kernel exact;
+  * k <= 0, runs on foreign streams, the plugin's single-process multi-GPU route (MCR_NUM_GPUS);
+  * the reference's own CUDA model (monte_carlos_cuda.cu compiled unmodified for sm_100a) as an independent-stream check.
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from mcr_b200 import api
+from mcr_b200.synthetic import synthetic_model
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+PKG = ROOT / "gpu-montecarlo-risk_b200"
+GOLD = ROOT / "tests" / "golden"
+
+
+@pytest.mark.parametrize("N,M", [(50, 100_000_000), (100, 30_000_000), (600, 20_000_000)])
+def test_fast_kernels_equal_the_fp64_kernel_at_full_size(engine, N, M):
+    """AUTO (tensor-core kernel + guard band + fp64 fix-up) == MCR_KERNEL_EXACT on (count, sum_S) over the full BASELINE
+    trial counts: 1e8 trials at N=50 (config 2), 2e7 at N=600 (config 4 shape), i.e. 5e9 / 1.2e10 per-asset decisions."""
+    m = synthetic_model(N)
+    engine.upload_sigma(m.mu, m.Sigma)
+    fast = engine.run(M, 67, m.x, m.k)
+    assert fast.kernel == "tensor"
+    exact = engine.run(M, 67, m.x, m.k, kernel=api.KERNEL_EXACT)
+    assert exact.kernel == "exact"
+    assert (fast.count, fast.sum_S, fast.n_paths) == (exact.count, exact.sum_S, M)
+    assert 0 < fast.n_rechecked < M // 20
+
+
+@pytest.mark.parametrize("N,M", [(50, 200_000), (100, 100_000), (128, 40_000), (160, 20_000), (320, 12_000), (600, 6_000)])
+@pytest.mark.parametrize("unit", [1e4, 1e-6, 1.0])
+def test_models_in_other_units_stay_exact(engine, oracle, N, M, unit):
+    """Returns in basis points (Sigma x 1e8, mu and x x 1e4) or tiny units (x 1e-6): the same events, so the per-trial S must
+    not change, whatever kernel AUTO picks.  A fixed operand scale overflows fp16 / drops into its subnormals here."""
+    m = synthetic_model(N)
+    A0 = engine.upload_sigma(m.mu, m.Sigma)
+    Z, _ = engine.dump_normals(M, 67)
+    base = oracle.run_normals(A0, m.mu, m.k, m.x, Z)
+    A = engine.upload_sigma(m.mu * unit, m.Sigma * unit * unit)
+    ro = oracle.run_normals(A, m.mu * unit, m.k, m.x * unit, Z)
+    h = api.simulate_host(m.mu * unit, A, M, 67, m.x * unit, m.k, a_is_lower=True, want_S_values=True)
+    assert h.kernel == "tensor"
+    np.testing.assert_array_equal(h.S_values, ro["S_values"])
+    assert (h.count, h.sum_S) == (ro["count"], ro["sum_S"])
+    # and the events are the same as in the original units up to fp64 rounding of the rescaled model
+    assert abs(ro["sum_S"] - base["sum_S"]) <= 2 + base["sum_S"] // 100000
+
+
+def test_rows_of_very_different_magnitude(engine, oracle):
+    """One asset quoted in basis points next to assets quoted as fractions: rows of the transform 1e4 apart."""
+    m = synthetic_model(64)
+    s = np.ones(64)
+    s[5], s[40], s[63] = 1e4, 1e-3, 3e2
+    mu, Sigma = m.mu * s, m.Sigma * np.outer(s, s)
+    # thresholds are per-model (one x): use x in the units of the unscaled assets; the scaled ones then (almost) never / always hit
+    A = engine.upload_sigma(mu, Sigma)
+    M = 200_000
+    Z, _ = engine.dump_normals(M, 67)
+    ro = oracle.run_normals(A, mu, m.k, m.x, Z)
+    for kernel in (api.KERNEL_TENSOR, api.KERNEL_FFMA, api.KERNEL_AUTO):
+        r = engine.run(M, 67, m.x, m.k, kernel=kernel)
+        assert (r.count, r.sum_S) == (ro["count"], ro["sum_S"]), r.kernel
+
+
+@pytest.mark.parametrize("N", [15, 50, 160, 600])
+def test_non_positive_k_counts_every_trial(engine, N):
+    """S >= k is a signed comparison in the reference (serial.c:137-141): k <= 0 counts every trial, on every kernel."""
+    m = synthetic_model(N)
+    engine.upload_sigma(m.mu, m.Sigma)
+    M = 50_000
+    want = engine.run(M, 67, m.x, 1, kernel=api.KERNEL_EXACT)
+    for kernel in (api.KERNEL_AUTO, api.KERNEL_EXACT) + ((api.KERNEL_FFMA,) if N <= 128 else ()):
+        for k in (0, -3):
+            r = engine.run(M, 67, m.x, k, kernel=kernel)
+            assert (r.count, r.sum_S) == (M, want.sum_S), (r.kernel, k)
+
+
+def test_runs_on_different_streams_are_ordered(engine):
+    """Every run of an engine shares its scratch buffers; a run enqueued on another stream waits for the previous one."""
+    import torch
+    m = synthetic_model(50)
+    engine.upload_sigma(m.mu, m.Sigma)
+    want = [engine.run(3_000_000, 67, m.x, m.k, path_offset=o) for o in (0, 3_000_000, 6_000_000)]
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    bufs = [torch.zeros(api.MCR_PARTIAL_WORDS, dtype=torch.int64, device="cuda") for _ in range(3)]
+    for rep in range(3):
+        for i, (s, b) in enumerate(zip(streams, bufs)):
+            engine.run_async(3_000_000, 67, m.x, m.k, b.data_ptr(), s.cuda_stream, path_offset=3_000_000 * i)
+        torch.cuda.synchronize()
+        for w, b in zip(want, bufs):
+            r = api.result_from_partials(b.cpu().numpy().astype(np.uint64))
+            assert (r.count, r.sum_S) == (w.count, w.sum_S)
+
+
+def test_mma_flops_accounting(engine):
+    m = synthetic_model(50)
+    engine.upload_sigma(m.mu, m.Sigma)
+    engine.run(10_000, 67, m.x, m.k)
+    assert engine.mma_flops_per_trial() == 3 * 2 * 64 * 64
+    engine.run(10_000, 67, m.x, m.k, kernel=api.KERNEL_FFMA)
+    assert engine.mma_flops_per_trial() == 0
+    m = synthetic_model(600)
+    engine.upload_sigma(m.mu, m.Sigma)
+    engine.run(10_000, 67, m.x, m.k)
+    f = engine.mma_flops_per_trial()
+    assert 3 * 600 * 601 <= f <= 3 * 2 * 640 * 640, f   # at least the triangle, at most the padded dense matrix, x3 passes
+
+
+# ---------------------------------------------------------------- the plugin's own multi-GPU route
+@pytest.mark.skipif(not (PKG / "libmcr_b200_model.so").exists(), reason="plugin not built")
+def test_plugin_multi_gpu_route_is_bit_identical(engine, monkeypatch):
+    """MCR_NUM_GPUS=2 through get_cuda_model (single process, ncclCommInitAll, one grouped all-reduce): same S_values / count
+    as one GPU, bit for bit.  Skipped on a single-GPU box; the driver's 2/4/8-GPU runs exercise the same route through
+    bench.py's e2e leg."""
+    if api.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    plugin = C.CDLL(str(PKG / "libmcr_b200_model.so"))
+    m = synthetic_model(50)
+    M = 3_000_001
+    monkeypatch.setenv("MCR_S_VALUES", "1")
+    monkeypatch.setenv("MCR_NUM_GPUS", "1")
+    one = oracle_lib.run_model_struct(plugin.get_cuda_model, m.mu, m.Sigma, m.k, m.x, M, 67)
+    monkeypatch.setenv("MCR_NUM_GPUS", "2")
+    two = oracle_lib.run_model_struct(plugin.get_cuda_model, m.mu, m.Sigma, m.k, m.x, M, 67)
+    assert one["rc"] == 0 and two["rc"] == 0
+    assert one["count"] == two["count"] and one["P_hat"] == two["P_hat"]
+    np.testing.assert_array_equal(one["S_values"], two["S_values"])
+    m6 = synthetic_model(600)
+    A = api.build_transform(m6.Sigma)
+    h1 = api.simulate_host(m6.mu, A, 400_000, 67, m6.x, m6.k, a_is_lower=True, n_gpus=1, want_hist=True)
+    h2 = api.simulate_host(m6.mu, A, 400_000, 67, m6.x, m6.k, a_is_lower=True, n_gpus=2, want_hist=True)
+    assert (h1.count, h1.sum_S) == (h2.count, h2.sum_S)
+    np.testing.assert_array_equal(h1.hist_S, h2.hist_S)
+
+
+# ---------------------------------------------------------------- the reference's own GPU model
+@pytest.mark.skipif(not oracle_lib.ref_cuda_path().exists(), reason="oracle/_ref/libref_cuda.so not built (reference tree absent at build time)")
+def test_reference_cuda_model_agrees_within_3_sigma(engine):
+    """monte_carlos_cuda.cu, compiled UNMODIFIED for sm_100a, against this library on the same model: independent RNG streams
+    (cuRAND XORWOW vs Philox), same lower-triangular transform -> P_hat within 3 sigma of the Monte Carlo standard error
+    (north-star check 2)."""
+    ref = oracle_lib.RefCuda()
+    for N, M in ((15, 2_000_000), (50, 4_000_000)):
+        if N == 15:
+            g = np.load(GOLD / "pyref_n15.npz")
+            mu, Sigma, x, k = g["mu"], g["Sigma"], 0.02, 5
+        else:
+            m = synthetic_model(N)
+            mu, Sigma, x, k = m.mu, m.Sigma, m.x, m.k
+        r = ref.cuda(mu, Sigma, k, x, M, 67)
+        assert r["rc"] == 0 and r["name"] == "cuda"
+        assert int((r["S_values"] >= k).sum()) == r["count"]
+        engine.upload_sigma(mu, Sigma, api.TRANSFORM_LOWER)
+        ours = engine.run(20_000_000, 67, x, k)
+        pr, po = r["P_hat"], ours.P_hat
+        se = np.sqrt(pr * (1 - pr) / M + po * (1 - po) / ours.n_paths)
+        assert abs(pr - po) <= 3 * se, (N, pr, po, se)
+        assert abs(r["S_values"].mean() - ours.sum_S / ours.n_paths) < 0.02 * max(r["S_values"].mean(), 1e-3) + 3e-3

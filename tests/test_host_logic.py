@@ -52,6 +52,48 @@ def test_loader_rejects_inconsistent_files(tmp_path):
         model_io.load_model(tmp_path)
 
 
+def test_c_loader_rejects_bad_files_before_touching_the_gpu(tmp_path):
+    """model_loader.c (the hardened twin of the reference's src/utilities/load_binary.c:13-36,56-87) through mcr_cli: every header /
+    length / dimension check runs before the first allocation, so the rejections need no GPU and name the offending file."""
+    import subprocess
+    exe = PKG / "bin" / "mcr_cli"
+    if not exe.exists():
+        pytest.skip("bin/mcr_cli not built")
+    m = synthetic_model(8)
+
+    def run(d):
+        return subprocess.run([str(exe), str(d), "1000"], capture_output=True, text=True, timeout=60)
+
+    cases = {}
+    d = tmp_path / "trunc_mu"; d.mkdir()
+    model_io.save_model(d, m.mu, m.Sigma, 0.0)
+    (d / "mu.bin").write_bytes((d / "mu.bin").read_bytes()[:-8])
+    cases["trunc_mu"] = (d, "mu.bin has the wrong length for N=8")
+    d = tmp_path / "trunc_sigma"; d.mkdir()
+    model_io.save_model(d, m.mu, m.Sigma, 0.0)
+    (d / "sigma.bin").write_bytes((d / "sigma.bin").read_bytes()[:-16])
+    cases["trunc_sigma"] = (d, "sigma.bin has the wrong length for a 8x8 matrix")
+    d = tmp_path / "mismatch"; d.mkdir()
+    model_io.save_model(d, m.mu[:7], m.Sigma, 0.0)
+    cases["mismatch"] = (d, "is 8x8 but")
+    d = tmp_path / "bad_header"; d.mkdir()
+    model_io.save_model(d, m.mu, m.Sigma, 0.0)
+    raw = bytearray((d / "mu.bin").read_bytes()); raw[0:4] = (-3).to_bytes(4, "little", signed=True)
+    (d / "mu.bin").write_bytes(bytes(raw))
+    cases["bad_header"] = (d, "Invalid dimension header")
+    d = tmp_path / "no_sigma"; d.mkdir()
+    model_io.save_model(d, m.mu, m.Sigma, 0.0)
+    (d / "sigma.bin").unlink()
+    cases["no_sigma"] = (d, "Cannot open")
+    d = tmp_path / "padded"; d.mkdir()
+    model_io.save_model(d, m.mu, m.Sigma, 0.0)
+    (d / "sigma.bin").write_bytes((d / "sigma.bin").read_bytes() + b"\0" * 8)   # trailing garbage is a length error too
+    cases["padded"] = (d, "wrong length")
+    for name, (d, msg) in cases.items():
+        p = run(d)
+        assert p.returncode == 1 and msg in p.stderr, (name, p.returncode, p.stderr)
+
+
 def test_shard_ranges_partition_the_path_range():
     for M, n in ((100, 1), (100, 3), (7, 8), (10**9, 8), (0, 4)):
         r = model_io.shard_ranges(M, n)

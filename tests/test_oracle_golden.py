@@ -100,6 +100,27 @@ def test_real_data_goldens(oracle):
     assert int((rf["S_values"] >= 5).sum()) == rf["count"]
 
 
+def test_goldens_do_not_depend_on_the_cholesky_diagonal_rounding(oracle):
+    """GSL is not installed here, and its Cholesky is restated from recall: the unblocked kernel scales the whole column
+    A(j:n, j), diagonal included, by 1/sqrt(a_jj) (what the shim, the oracle and mcr_build_transform do); a build that stored
+    L_jj = sqrt(a_jj) instead would differ by at most one ulp on the diagonal.  Per-trial S over the whole C1 run is the same
+    either way, so the frozen counts are not an artefact of that choice."""
+    g = np.load(GOLD / "pyref_n15.npz")
+    differ = 0
+    for mode in (oracle_lib.GSL_FULL, oracle_lib.LOWER):
+        A0 = oracle.transform(g["Sigma"], mode)
+        A1 = oracle.transform(g["Sigma"], mode | oracle_lib.DIAG_SQRT)
+        off = ~np.eye(15, dtype=bool)
+        assert np.array_equal(A0[off], A1[off])
+        d0, d1 = np.diag(A0), np.diag(A1)
+        assert np.all(np.abs(d0 - d1) <= np.spacing(d1))
+        differ += int((d0 != d1).sum())
+        r0 = oracle.run_mt19937(A0, g["mu"], 5, 0.02, 1000000, 67)
+        r1 = oracle.run_mt19937(A1, g["mu"], 5, 0.02, 1000000, 67)
+        np.testing.assert_array_equal(r0["S_values"], r1["S_values"])
+    print(f"diagonal entries that differ by one ulp between the two roundings: {differ} of 30")
+
+
 @pytest.mark.skipif(not oracle_lib.ref_models_path().exists(), reason="oracle/_ref not built (reference tree absent)")
 def test_oracle_matches_compiled_reference_models(oracle):
     """The reference's monte_carlo_serial.c / monte_carlo_omp.c, compiled unmodified against the GSL shim."""
