@@ -201,7 +201,7 @@ int mcr_destroy(mcr_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_mu); cudaFree(e->d_Acm); cudaFree(e->d_tc_image); cudaFree(e->d_slab_image); cudaFree(e->d_S_acc);
-    cudaFree(e->d_pair_list); cudaFree(e->d_pair_count); cudaFree(e->d_Arm); cudaFree(e->d_wide_image); cudaFree(e->d_wide_c);
+    cudaFree(e->d_pair_list); cudaFree(e->d_pair_count); cudaFree(e->d_Arm); cudaFree(e->d_wide_image); cudaFree(e->d_wide_c); cudaFree(e->d_stream_image);
     cudaFree(e->d_flag_list); cudaFree(e->d_flag_count); cudaFree(e->d_accum);
     cudaFree(e->d_block_partials); cudaFree(e->d_partials);
     cudaFree(e->d_port_acc); cudaFree(e->d_port_hist); cudaFree(e->d_port_hist_sum);
@@ -291,7 +291,8 @@ struct RunPlan {
     bool recheck;
     bool portfolio;   // accumulator row N carries the portfolio return (tensor kernel only)
     bool slab;        // N > 128: tensor kernel over row slabs of 256 assets (MCR_LARGE_N=slab)
-    bool wide;        // N > 128: single-pass tensor kernel, all accumulators in TMEM (default)
+    bool wide;        // N > 128: single-pass tensor kernel of round 1 (MCR_LARGE_N=wide)
+    bool stream;      // streamed tensor kernel: normals in TMEM, passes over row ranges (N > 128 by default; supplied normals)
     int rows;         // accumulator rows needed: N (+1 with the portfolio row)
 };
 
@@ -311,14 +312,15 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
     plan->portfolio = opt && opt->want_portfolio;
     plan->slab = false;
     plan->rows = e->N + (plan->portfolio ? 1 : 0);
-    if (!normals && !plan->portfolio && e->N > tc_max_n() && (want == MCR_KERNEL_AUTO || want == MCR_KERNEL_TENSOR)) {
-        // two kernels for N > 128 (profiles/r01_large_n_sweep.log): the single-pass kernel wins where 3..5 slabs of 128 rows
-        // fill TMEM with tiles of 96-128 trials (257 <= N <= 640); elsewhere the row-slab kernel does.  MCR_LARGE_N=slab|wide forces one.
+    if (!plan->portfolio && (e->N > tc_max_n() || normals) && (want == MCR_KERNEL_TENSOR || (want == MCR_KERNEL_AUTO && e->N > tc_max_n())) &&
+        stream_supported(e->N)) {
+        // N > 128, and every supplied-normals run that asks for the tensor path: the streamed kernel (mcr_stream.cu).  The two
+        // round-1 kernels stay selectable for A/B runs: MCR_LARGE_N=slab|wide (generated normals only).
         static const int forced = [] { const char* v = getenv("MCR_LARGE_N"); return !v ? 0 : !strcmp(v, "slab") ? 1 : !strcmp(v, "wide") ? 2 : 0; }();
         plan->kernel = MCR_KERNEL_TENSOR;
-        const bool wide_wins = wide_slabs(e->N) >= 3 && wide_slabs(e->N) <= 5;
-        if (wide_supported(e->N) && (forced == 2 || (forced == 0 && wide_wins))) { plan->wide = true; plan->NT = 128 * wide_slabs(e->N); }
-        else { plan->slab = true; plan->NT = slab_rows() * slab_count(e->N); }
+        if (!normals && e->N > tc_max_n() && forced == 2 && wide_supported(e->N)) { plan->wide = true; plan->NT = 128 * wide_slabs(e->N); }
+        else if (!normals && e->N > tc_max_n() && forced == 1) { plan->slab = true; plan->NT = slab_rows() * slab_count(e->N); }
+        else { plan->stream = true; plan->NT = (e->N + 15) & ~15; }
         return 0;
     }
     const bool tc_ok = !normals && tc_supported(plan->rows);
@@ -330,7 +332,6 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
         return 0;
     }
     if (want == MCR_KERNEL_TENSOR) {
-        if (normals) return fail("the tensor-core kernel generates its normals in-kernel; use the FFMA or EXACT kernel with supplied normals");
         if (!tc_ok) return fail("tensor-core kernel covers N <= %d in this build (N=%d)", tc_max_n(), e->N);
         plan->kernel = MCR_KERNEL_TENSOR; plan->NT = tc_padded_n(plan->rows);
         return 0;
@@ -449,7 +450,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
 
     TcLaunch tl{};
     int tc_grid_full = 0;
-    if (plan.kernel == MCR_KERNEL_TENSOR && !plan.slab && !plan.wide) {
+    if (plan.kernel == MCR_KERNEL_TENSOR && !plan.slab && !plan.wide && !plan.stream) {
         // split, swizzled transform image (depends on x through the constant column): rebuilt only when
         // the model or x changed
         const int rows = plan.rows;
@@ -524,7 +525,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
     }
 
     // ---- row-slab tensor path (N > 128): per-slab images, per-trial uint16 accumulator ----
-    const uint64_t chunk_paths = (plan.slab || plan.wide) ? SLAB_CHUNK_PATHS : CHUNK_PATHS;
+    const uint64_t chunk_paths = (plan.slab || plan.wide || plan.stream) ? SLAB_CHUNK_PATHS : CHUNK_PATHS;
     std::vector<double> slab_drel, slab_dabs;
     if (plan.slab) {
         const int ns = slab_count(N);
@@ -614,6 +615,53 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         wl.block_partials = e->d_block_partials;
     }
 
+    // ---- streamed tensor path: piece image, per-pass guard bands ----
+    StreamLaunch stl{};
+    if (plan.stream) {
+        const size_t bytes = stream_image_bytes(N, e->lower);
+        if (e->stream_image_cap < bytes) {
+            cudaFree(e->d_stream_image); e->d_stream_image = nullptr; e->stream_image_cap = 0;
+            MCR_CUDA(cudaMalloc(&e->d_stream_image, bytes));
+            e->stream_image_cap = bytes; e->stream_gen = 0;
+        }
+        std::vector<double> c(N);
+        for (int i = 0; i < N; ++i) c[i] = e->mu[i] + x;
+        if (e->stream_gen != e->gen || e->stream_x != x) {
+            e->stream_host_image.resize(bytes);
+            e->stream_row_scale.assign(N, 1.0);
+            stream_build(N, e->lower, e->A.data(), c.data(), e->stream_host_image.data(), e->stream_row_scale.data());
+            MCR_CUDA(cudaStreamSynchronize(s));   // a previous run may still read the old image
+            MCR_CUDA(cudaMemcpyAsync(e->d_stream_image, e->stream_host_image.data(), bytes, cudaMemcpyHostToDevice, s));
+            e->stream_gen = e->gen; e->stream_x = x;
+        }
+        // guard band per pass, same budget as the round-1 large-N kernels: fp16x3 split (3 * 2^-22) + fp32 accumulation over 12 MMAs
+        // per K-block, relative to ||a_i||_2 ||z||_2 (Cauchy-Schwarz; the kernel tracks the norm of the pass's normals), in
+        // accumulator units (row i scaled by stream_row_scale[i]); derivation in DESIGN.md section 3.1
+        static const double band_scale = [] { const char* v = getenv("MCR_TC_BAND_SCALE"); return v && *v ? atof(v) : 1.0; }();
+        StreamPass ps[STREAM_MAX_PASSES];
+        const int np = stream_plan(N, e->lower, ps);
+        for (int q = 0; q < np; ++q) {
+            const double gamma = std::ldexp(1.0, -19) * std::max(1.0, ps[q].kbn / 8.0);
+            double rownorm = 0, cabs = 1e-300;
+            for (int i = ps[q].r0; i < std::min(N, ps[q].r0 + ps[q].W); ++i) {
+                double ss = 0;
+                for (int j = 0; j < N; ++j) ss += e->A[(size_t)i * N + j] * e->A[(size_t)i * N + j];
+                rownorm = std::max(rownorm, std::sqrt(ss) * e->stream_row_scale[i]);
+                cabs = std::max(cabs, std::fabs(c[i]) * e->stream_row_scale[i]);
+            }
+            stl.delta_rel[q] = plan.recheck ? band_scale * 2.0 * gamma * rownorm : 0.0;
+            stl.delta_abs[q] = plan.recheck ? band_scale * 2.0 * gamma * cabs + 1e-30 : 0.0;
+        }
+        mma_flops = stream_mma_flops(N, e->lower);
+        stl.key0 = key0; stl.key1 = key1; stl.N = N; stl.k = k; stl.lower = e->lower ? 1 : 0;
+        stl.d_image = e->d_stream_image;
+        stl.flag_list = e->d_flag_list; stl.flag_count = e->d_flag_count; stl.flag_cap = FLAG_CAP;
+        // supplied normals: exact_pairs_kernel re-derives its normals from Philox, so every near-threshold trial takes the
+        // whole-trial fp64 kernel (which reads the caller's normals)
+        stl.pair_list = (plan.recheck && !dZ) ? e->d_pair_list : nullptr; stl.pair_count = e->d_pair_count; stl.pair_cap = PAIR_CAP;
+        stl.block_partials = e->d_block_partials;
+    }
+
     for (uint64_t done = 0; done < M || (M == 0 && done == 0); done += chunk_paths) {
         const uint64_t m = std::min<uint64_t>(chunk_paths, M - done);
         if (m == 0) break;
@@ -665,6 +713,30 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             fin.block_partials = e->d_block_partials; fin.n_blocks = grid;
             fin.flag_count = e->d_flag_count; fin.flag_cap = FLAG_CAP;
             if (plan.recheck) { fin.pair_count = e->d_pair_count; fin.pair_cap = PAIR_CAP; }
+        } else if (plan.stream) {
+            stl.M = m; stl.path_offset = path_offset + done; stl.S_out = xp.S_out; stl.d_Z = xp.Z;
+            const bool timed = e->n_timed < MAX_TIMED_CHUNKS;
+            if (timed) MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed], s));
+            MCR_CUDA(stream_launch(stl, e->num_sms, s));
+            if (timed) { MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed + 1], s)); ++e->n_timed; }
+            ++launches;
+            if (plan.recheck) {
+                if (stl.pair_list) {
+                    PairParams pp{};
+                    pp.pair_list = e->d_pair_list; pp.pair_count = e->d_pair_count; pp.pair_cap = PAIR_CAP;
+                    pp.path_offset = path_offset + done; pp.key0 = key0; pp.key1 = key1;
+                    pp.N = N; pp.lower = e->lower ? 1 : 0; pp.x = x; pp.mu = e->d_mu; pp.A_rm = e->d_Arm;
+                    pp.k = k; pp.S_out = xp.S_out; pp.accum = e->d_accum; pp.mode = 2;
+                    MCR_CUDA(launch_exact_pairs(pp, e->num_sms, s));
+                    ++launches;
+                    fin.pair_count = e->d_pair_count; fin.pair_cap = PAIR_CAP;
+                }
+                xp.flag_list = e->d_flag_list; xp.flag_count = e->d_flag_count; xp.flag_cap = FLAG_CAP;
+                MCR_CUDA(launch_exact(xp, e->num_sms, s));
+                ++launches;
+            }
+            fin.block_partials = e->d_block_partials; fin.n_blocks = stream_grid(m, e->num_sms);
+            fin.flag_count = e->d_flag_count; fin.flag_cap = FLAG_CAP;
         } else if (plan.wide) {
             wl.M = m; wl.path_offset = path_offset + done; wl.S_out = xp.S_out;
             const bool timed = e->n_timed < MAX_TIMED_CHUNKS;

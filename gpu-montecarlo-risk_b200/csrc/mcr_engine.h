@@ -65,6 +65,13 @@ struct mcr_engine {
     std::vector<uint8_t> wide_host_image;
     std::vector<float> wide_host_c;
     std::vector<double> wide_row_scale;
+    // streamed tensor path (N > 128 by default; any N with supplied normals)
+    void* d_stream_image = nullptr;
+    size_t stream_image_cap = 0;
+    uint64_t stream_gen = 0;
+    double stream_x = 0;
+    std::vector<uint8_t> stream_host_image;
+    std::vector<double> stream_row_scale;
     unsigned long long* d_pair_list = nullptr;   // single near-threshold (trial, row) decisions of a chunk
     uint32_t* d_pair_count = nullptr;
     double* d_Arm = nullptr;                     // fp64 transform, row-major (per-decision fix-up)

@@ -191,6 +191,35 @@ void wide_build(int N, bool lower, const double* A, const double* c, uint8_t* im
 int wide_grid(uint64_t M, int N, int num_sms);
 cudaError_t wide_launch(const WideLaunch& l, int num_sms, cudaStream_t s);
 
+// ---- streamed tensor-core path: M = trials, normals in TMEM, passes over row ranges (mcr_stream.cu) -----------------
+constexpr int STREAM_WMAX = 384;        // transform rows (accumulator columns) per pass
+constexpr int STREAM_MAX_PASSES = 4;    // N <= 1024 is at most 3 passes
+struct StreamPass { int32_t r0, W, kbn, kend; };   // rows [r0, r0 + W), K-blocks, normal columns [0, kend)
+struct StreamLaunch {
+    uint64_t M, path_offset;
+    uint32_t key0, key1;
+    int32_t N, k, lower;
+    const void* d_image;         // stream_build image on the device
+    const double* d_Z;           // supplied normals (M x N fp64, chunk-relative) or nullptr: Philox
+    double delta_rel[STREAM_MAX_PASSES], delta_abs[STREAM_MAX_PASSES];   // guard band per pass (relative to ||z||_2), accumulator units
+    int32_t* S_out;
+    uint32_t* flag_list;
+    uint32_t* flag_count;
+    uint32_t flag_cap;
+    unsigned long long* pair_list;   // trial << 21 | other hits << 10 | row, or nullptr
+    uint32_t* pair_count;
+    uint32_t pair_cap;
+    uint64_t* block_partials;
+};
+bool stream_supported(int N);
+int stream_plan(int N, bool lower, StreamPass* pass /* STREAM_MAX_PASSES */);   // number of passes
+size_t stream_image_bytes(int N, bool lower);
+double stream_mma_flops(int N, bool lower);          // fp16 MMA flops issued per trial
+int stream_normals_per_trial(int N, bool lower);     // normals generated per trial (passes re-derive the leading columns)
+void stream_build(int N, bool lower, const double* A, const double* c, uint8_t* image, double* row_scale /* N, out */);
+int stream_grid(uint64_t M, int num_sms);
+cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s);
+
 cudaError_t launch_hist(uint64_t M, const int32_t* S, int nbins, unsigned long long* hist, int num_sms, cudaStream_t s);
 cudaError_t launch_dump(uint64_t M, uint64_t path_offset, uint32_t key0, uint32_t key1, int N,
                         float* dZ, uint32_t* dU, cudaStream_t s);

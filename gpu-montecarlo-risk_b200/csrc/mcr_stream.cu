@@ -1,0 +1,593 @@
+// Streamed tensor-core kernel for wide portfolios (128 < N <= 1024: the Stoxx600 shape; any N with supplied normals).
+//
+// Round 1 had two kernels here.  The single-pass kernel (mcr_wide.cu) turns the GEMM around (M = 128 transform rows, N = 96
+// trials) so that all accumulators fit TMEM, and is bound by shared-memory bandwidth: every MMA re-reads a 4 KB transform
+// tile, 10.4 KB of shared-memory traffic per MMA in all, 109 clocks per MMA against the nominal 48
+// (profiles/r01_wide_n600_after_fix_ncu_summary.txt, r02_ubench_umma_ts.log).  The row-slab kernel (mcr_tc.cu) keeps
+// M = trials but re-derives the normals once per 256-row slab.  This kernel keeps what works in each:
+//
+//     D[128 trials x W assets] += Z_kb[128 x 64] * B_{p,kb}[W x 64]^T            (tcgen05.mma, M = 128, N <= 256, K = 16)
+//
+//   * M = trials.  The A operand IS the block of normals, and it lives in TMEM (".ts" form): the generator threads write their
+//     trial's fp16 hi / lo pairs straight into the tile with tcgen05.st (lane = trial; no swizzle arithmetic, no shared-memory
+//     traffic, no proxy fence).  Measured: with A in TMEM an N >= 192 MMA retires at the nominal N / 2 clocks.
+//   * Shared memory holds nothing but the ring of transform pieces streaming from L2 (cp.async.bulk + mbarrier, 4 x 48 KB).
+//   * TMEM: 2 Z slots of 64 columns (32 hi + 32 lo) + up to 384 accumulator columns.  A model with more rows than that is done
+//     in passes over row ranges; pass p only needs the normals of columns [0, kend_p), which are re-derived from the
+//     counter-based stream: 224 + 600 normals per trial at N = 600 (lower-triangular), against 600 in the single-pass kernel
+//     and 1368 in the row-slab kernel.  N <= 384 is a single pass.
+//   * Lower-triangular transforms: K-block kb only multiplies the rows >= 64 kb (16-row granularity: the MMA's N and the
+//     accumulator column offset shrink with kb), so the tensor pipe executes 1.2x the triangle instead of 1.6x.
+//   * The constant mu_i + x enters as the first MMA of a pass (which therefore also initialises the accumulators): a Z slot
+//     holding ones in K columns 0, 1 times a piece holding the hi and lo halves of the scaled constants.
+//   * fp16 x 3 as everywhere: Zhi Bhi + Zlo Bhi + Zhi Blo, fp32 accumulate.  The hi piece of a K-block is consumed by the
+//     first two products and released before the lo piece is needed.
+//   * Epilogue in the same threads: lane = trial, so a thread counts the sign bits of its own row; the two smallest
+//     |accumulator| keys of the row decide between "no decision near the threshold", "exactly one" (that row alone goes to
+//     exact_pairs_kernel) and "several" (the whole trial goes to the fp64 kernel), exactly like the row-slab kernel.
+//   * SUPPLIED = true: the normals come from the caller (M x N fp64 in HBM, serial.c:67-69 layout) instead of Philox:
+//     parity mode 1 "fed identical pre-generated normals through the interface" reaches the tensor path.
+#include "../../include/mcr_b200.h"
+#include "mcr_internal.h"
+#include "mcr_rng.cuh"
+#include "mcr_tc_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace mcr {
+
+// tuning only (tools/devbuild_one.sh), a bit mask: 1 = the loader copies each ring slot once and then only signals it (no transform
+// stream from L2), 2 = the generators skip Philox / Box-Muller (garbage normals), 4 = the MMA warp commits without issuing MMAs.
+// Results are garbage; run with no_recheck.
+#ifndef MCR_STREAM_ABLATE
+#define MCR_STREAM_ABLATE 0
+#endif
+
+constexpr int ST_WMAX = STREAM_WMAX;                 // accumulator columns = transform rows per pass
+constexpr int ST_ZSLOTS = 2;
+constexpr int ST_ZCOLS = 64;                         // TMEM columns of a Z slot: 32 (hi pairs) + 32 (lo pairs)
+constexpr int ST_ACC_COL = ST_ZSLOTS * ST_ZCOLS;     // first accumulator column
+constexpr int ST_CHUNK_MAX = 256;                    // rows of one transform piece = the N of the MMAs that read it
+constexpr uint32_t ST_PIECE_MAX = ST_CHUNK_MAX * 128;   // 32 KB: up to 256 rows x 64 fp16
+constexpr int ST_RING_MAX = 6;                       // transform pieces in flight (6 x 32 KB; 3 when the Z cache takes its share)
+constexpr int ST_KCACHE_MAX = 3;                     // K-blocks of normals kept in shared memory for the later passes (32 KB each)
+constexpr uint32_t ST_ZCACHE_BYTES = 128 * 64 * 4;   // one K-block of Z: 128 trials x 64 columns x (hi + lo)
+constexpr int ST_PARTS = 4;                          // generator threads per trial: 16 of a K-block's 64 columns each
+constexpr int ST_GEN_THREADS = 128 * ST_PARTS;
+constexpr int ST_THREADS = ST_GEN_THREADS + 64;      // + MMA-issue warp + loader warp
+constexpr int ST_MMA_WARP = ST_GEN_THREADS / 32, ST_LOAD_WARP = ST_MMA_WARP + 1;
+constexpr int ST_ALL = ST_GEN_THREADS + 32;          // generators + MMA warp
+constexpr int ST_BAR_SLOT = 1, ST_BAR_ACC = 3, ST_BAR_GEN = 4;   // named barriers: 1, 2 = Z slot full; accumulators free; generators only
+constexpr uint32_t ST_KEY_MASK = 0xFFFFFC00u;        // epilogue keys: bits 10.. = |accumulator| << 1 (truncated), 1..9 = column, 0 = sign
+static_assert(ST_ACC_COL + ST_WMAX <= 512, "TMEM columns");
+static_assert(ST_RING_MAX * ST_PIECE_MAX + 1024 <= 220 * 1024 && (ST_RING_MAX - ST_KCACHE_MAX) * ST_PIECE_MAX + ST_KCACHE_MAX * ST_ZCACHE_BYTES + 1024 <= 220 * 1024,
+              "shared memory");
+
+struct StreamParams {
+    uint64_t M, path_offset;
+    uint32_t key0, key1;
+    int32_t N, k, lower, npass;
+    int32_t ring;              // ring slots in use
+    int32_t kcache;            // K-blocks 0 .. kcache - 1 of a tile's normals are kept in shared memory after the first pass
+    StreamPass pass[STREAM_MAX_PASSES];
+    float delta_rel[STREAM_MAX_PASSES], delta_abs[STREAM_MAX_PASSES], thr_max[STREAM_MAX_PASSES];   // accumulator units
+    const uint8_t* image;      // pieces in consumption order (stream_build)
+    const double* Z;           // SUPPLIED: M x N fp64 row-major (chunk-relative), else nullptr
+    int32_t* S_out;
+    uint32_t* flag_list;
+    uint32_t* flag_count;
+    uint32_t flag_cap;
+    unsigned long long* pair_list;   // trial << 21 | other hits << 10 | row, or nullptr
+    uint32_t* pair_count;
+    uint32_t pair_cap;
+    uint64_t* block_partials;
+};
+
+// first accumulator column K-block kb multiplies in a pass starting at row r0 (rows < 64 kb of a lower-triangular transform are
+// zero in these columns); r0 and 64 kb are multiples of 16, so the MMA's N stays a multiple of 16
+__host__ __device__ inline int stream_acol0(int r0, int kb, int lower) {
+    const int a = lower ? 64 * kb - r0 : 0;
+    return a > 0 ? a : 0;
+}
+// an active width w <= 384 as one or two chunks (one transform piece and one MMA N each; <= 256, multiple of 16)
+__host__ __device__ inline int stream_n1(int w) { return w <= ST_CHUNK_MAX ? w : ((w / 2 + 15) & ~15); }
+
+namespace tc {
+// D[tmem] (+)= A[tmem] * B[smem desc]^T: the A operand (128 lanes x 8 columns of fp16 pairs per K-step) comes from tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_store_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_st(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_st(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+}  // namespace tc
+
+// 16 normals -> 8 + 8 packed fp16 pairs (hi, lo); same split as store_chunk: hi = rn16(z), lo = rn16(z - hi)
+__device__ __forceinline__ void split16(const float (&z)[16], uint32_t (&hv)[8], uint32_t (&lv)[8]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const __half2 h = __floats2half2_rn(z[2 * q], z[2 * q + 1]);
+        hv[q] = *reinterpret_cast<const uint32_t*>(&h);
+        const __half2 l = __floats2half2_rn(sub_half(z[2 * q], (unsigned short)(hv[q] & 0xffffu)), sub_half(z[2 * q + 1], (unsigned short)(hv[q] >> 16)));
+        lv[q] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+}
+
+template <bool SUPPLIED>
+__global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* s_ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // [ring][ST_PIECE_MAX]
+    const int RING = p.ring;
+    uint4* s_zcache = reinterpret_cast<uint4*>(s_ring + (size_t)RING * ST_PIECE_MAX);   // [kcache][part][4][128 rows] x 16 B
+    __shared__ uint64_t s_zempty[ST_ZSLOTS], s_bfull[ST_RING_MAX], s_bempty[ST_RING_MAX], s_done;
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_part_S[ST_PARTS][128], s_part_k1[ST_PARTS][128], s_part_k2[ST_PARTS][128];
+    __shared__ float s_part_zsq[ST_PARTS][128];
+    __shared__ uint32_t s_cnt[4], s_sum[4];
+
+    // the warp index through a shuffle: warp-uniform for the compiler (role loops keep their state in uniform registers)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    if (tid == 0) {
+        for (int b = 0; b < ST_ZSLOTS; ++b) mbar_init(&s_zempty[b], 1);
+        for (int b = 0; b < ST_RING_MAX; ++b) { mbar_init(&s_bfull[b], 1); mbar_init(&s_bempty[b], 1); }
+        mbar_init(&s_done, 1);
+    }
+    if (warp == ST_MMA_WARP) tmem_alloc(&s_tmem, 512);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+
+    const uint64_t n_tiles = (p.M + TILE_M - 1) / TILE_M;
+    const uint64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int NPASS = p.npass, LOWER = p.lower;
+
+    if (warp == ST_MMA_WARP) {
+        // ---- MMA issue: per pass the constant slot, then the K-blocks in order.  A K-block arrives as one hi and one lo piece per
+        // chunk of <= 256 rows; a hi piece is multiplied by Zhi and Zlo, a lo piece by Zhi, and each is released right after ----
+        uint32_t zu = 0, rs = 0, rphase = 0;
+        auto next_piece = [&]() { if (++rs == (uint32_t)RING) { rs = 0; rphase ^= 1u; } };
+        for (uint64_t n = 0; n < my_tiles; ++n) {
+            for (int ps = 0; ps < NPASS; ++ps) {
+                const int r0 = p.pass[ps].r0, W = p.pass[ps].W, KBN = p.pass[ps].kbn;
+                for (int kb = -1; kb < KBN; ++kb, ++zu) {
+                    const uint32_t slot = zu & 1u;
+                    named_bar_sync(ST_BAR_SLOT + slot, ST_ALL);            // the Z slot is written (tcgen05.st waited for, fenced)
+                    if (kb < 0) named_bar_sync(ST_BAR_ACC, ST_ALL);        // the previous pass has been read out of the accumulators
+                    const int acol0 = kb < 0 ? 0 : stream_acol0(r0, kb, LOWER);
+                    const int w = W - acol0, n1 = stream_n1(w), n2 = w - n1;
+                    const uint32_t a_hi = tmem_base + slot * ST_ZCOLS, a_lo = a_hi + 32u;
+                    const uint32_t d1 = tmem_base + (uint32_t)(ST_ACC_COL + acol0);
+                    for (int half = 0; half < (kb < 0 ? 1 : 2); ++half) {
+                        for (int c = 0; c < (n2 > 0 ? 2 : 1); ++c) {
+                            const uint32_t d = c ? d1 + (uint32_t)n1 : d1;
+                            const uint32_t id = make_idesc(c ? n2 : n1);
+                            const bool last = half == (kb < 0 ? 0 : 1) && c == (n2 > 0 ? 1 : 0);
+                            mbar_wait(&s_bfull[rs], rphase);
+                            if (elect_one()) {
+                                tc_fence_after();
+                                const uint64_t b = make_desc(smem_u32(s_ring + rs * ST_PIECE_MAX));
+                                if (!(MCR_STREAM_ABLATE & 4)) {
+                                    if (kb < 0) {   // constants: ones (K columns 0, 1) x [hi | lo] of (mu_i + x) s_i; initialises the accumulators
+                                        umma_f16_ts(d, a_hi, b, id, 0u);
+                                    } else if (half == 0) {   // hi piece: Zhi Bhi, then Zlo Bhi
+#pragma unroll
+                                        for (int ks = 0; ks < KBLOCK / 16; ++ks) umma_f16_ts(d, a_hi + 8 * ks, b + 2 * ks, id, 1u);
+#pragma unroll
+                                        for (int ks = 0; ks < KBLOCK / 16; ++ks) umma_f16_ts(d, a_lo + 8 * ks, b + 2 * ks, id, 1u);
+                                    } else {                  // lo piece: Zhi Blo
+#pragma unroll
+                                        for (int ks = 0; ks < KBLOCK / 16; ++ks) umma_f16_ts(d, a_hi + 8 * ks, b + 2 * ks, id, 1u);
+                                    }
+                                }
+                                umma_commit(&s_bempty[rs]);
+                                if (last) {
+                                    umma_commit(&s_zempty[slot]);
+                                    if (kb == KBN - 1) umma_commit(&s_done);
+                                }
+                            }
+                            __syncwarp();
+                            next_piece();
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == ST_LOAD_WARP) {
+        // ---- transform loader: the same sequence of pieces for every tile ----
+        if (lane == 0) {
+            uint32_t rs = 0, rphase = 0, piece = 0;
+            for (uint64_t n = 0; n < my_tiles; ++n) {
+                const uint8_t* src = p.image;
+                for (int ps = 0; ps < NPASS; ++ps) {
+                    const int r0 = p.pass[ps].r0, W = p.pass[ps].W, KBN = p.pass[ps].kbn;
+                    for (int kb = -1; kb < KBN; ++kb) {
+                        const int w = W - (kb < 0 ? 0 : stream_acol0(r0, kb, LOWER)), n1 = stream_n1(w), n2 = w - n1;
+                        for (int half = 0; half < (kb < 0 ? 1 : 2); ++half)
+                            for (int c = 0; c < (n2 > 0 ? 2 : 1); ++c, ++piece) {
+                                const uint32_t bytes = (uint32_t)(c ? n2 : n1) * 128u;
+                                if (piece >= (uint32_t)RING) mbar_wait(&s_bempty[rs], rphase ^ 1u);
+                                if ((MCR_STREAM_ABLATE & 1) && piece >= (uint32_t)RING) {
+                                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_bfull[rs])) : "memory");
+                                } else {
+                                    mbar_expect_tx_st(&s_bfull[rs], bytes);
+                                    bulk_g2s_st(smem_u32(s_ring + rs * ST_PIECE_MAX), src, bytes, &s_bfull[rs]);
+                                }
+                                src += bytes;
+                                if (++rs == (uint32_t)RING) { rs = 0; rphase ^= 1u; }
+                            }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- generator + epilogue warps: warp w owns TMEM lanes 32 (w % 4) .. +31 (trial rows) and columns 16 (w / 4) .. +15 of a K-block ----
+        const int quarter = warp & 3, part = warp >> 2, row = 32 * quarter + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * quarter) << 16);
+        const int KCACHE = SUPPLIED ? 0 : p.kcache;
+        uint32_t zu = 0, done_parity = 0, cnt = 0, sum_s = 0;
+        // state of the trial in this thread's row across the passes of a tile (kept by the part-0 thread of the row)
+        uint32_t S_tot = 0, n_amb = 0, amb = 0;
+
+        // Read one pass out of the accumulators: per 32-column group (dealt round-robin to the four parts of the row) the sign
+        // bits and, where anything can be inside the band, the two smallest keys; combined per row in shared memory.
+        auto epilogue = [&](int ps, float zsq, uint64_t i, bool last_of_tile, bool more_work) {
+            mbar_wait<64>(&s_done, done_parity);
+            done_parity ^= 1u;
+            tc_fence_after();
+            const int W = p.pass[ps].W, r0 = p.pass[ps].r0;
+            const float thr_max = p.thr_max[ps];
+            uint32_t S = 0, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+#pragma unroll 1
+            for (int c0 = 32 * part; c0 < W; c0 += 32 * ST_PARTS) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + (uint32_t)(ST_ACC_COL + c0), v);
+                tmem_ld_wait();
+                const int valid = W - c0;    // a multiple of 16: the last group of a pass may hold only 16 columns
+                float m = 3.0e38f;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if (c < 16 || valid > 16) {
+                        S += v[c] >> 31;
+                        m = fminf(m, fabsf(__uint_as_float(v[c])));
+                    }
+                }
+                if (m < thr_max) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if (c < 16 || valid > 16) {
+                            const uint32_t key = (__funnelshift_l(v[c], v[c], 1) & (ST_KEY_MASK | 1u)) | ((uint32_t)(c0 + c) << 1);
+                            k2 = min(k2, max(k1, key));
+                            k1 = min(k1, key);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            if (more_work) named_bar_arrive(ST_BAR_ACC, ST_ALL);   // the MMA warp may overwrite the accumulators (next pass)
+            s_part_S[part][row] = S;
+            s_part_k1[part][row] = k1;
+            s_part_k2[part][row] = k2;
+            s_part_zsq[part][row] = zsq;
+            named_bar_sync(ST_BAR_GEN, ST_GEN_THREADS);
+            if (part == 0) {
+                uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;
+                float zz = 0.0f;
+                S = 0;
+#pragma unroll
+                for (int q = 0; q < ST_PARTS; ++q) {
+                    S += s_part_S[q][row];
+                    zz += s_part_zsq[q][row];
+                    const uint32_t a = s_part_k1[q][row], b = s_part_k2[q][row];
+                    m2 = min(m2, max(m1, a)); m1 = min(m1, a);
+                    m2 = min(m2, max(m1, b)); m1 = min(m1, b);
+                }
+                const float thr = __fmaf_rn(p.delta_rel[ps], sqrtf(zz) * 1.0001f, p.delta_abs[ps]);
+                const uint32_t thr_key = __float_as_uint(thr) << 1;
+                if ((m1 & ST_KEY_MASK) < thr_key) {
+                    if ((m2 & ST_KEY_MASK) < thr_key) {
+                        n_amb += 2u;
+                    } else {
+                        if (n_amb == 0u) amb = ((uint32_t)(r0 + (int)((m1 >> 1) & 0x1FFu)) << 1) | (m1 & 1u);
+                        n_amb += 1u;
+                        S -= m1 & 1u;        // the uncertain decision is left out of S; exact_pairs_kernel adds the fp64 one
+                    }
+                }
+                S_tot += S;
+                if (last_of_tile) {
+                    if (i < p.M) {
+                        if (n_amb == 0u) {
+                            cnt += (S_tot >= (uint32_t)p.k) ? 1u : 0u;
+                            sum_s += S_tot;
+                            if (p.S_out) p.S_out[i] = (int32_t)S_tot;
+                        } else if (n_amb == 1u && p.pair_list) {
+                            const uint32_t slot = atomicAdd(p.pair_count, 1u);
+                            if (slot < p.pair_cap)
+                                p.pair_list[slot] = ((unsigned long long)i << 21) | ((unsigned long long)S_tot << 10) | (unsigned long long)(amb >> 1);
+                        } else {
+                            const uint32_t slot = atomicAdd(p.flag_count, 1u);
+                            if (slot < p.flag_cap) p.flag_list[slot] = (uint32_t)i;
+                        }
+                    }
+                    S_tot = 0u; n_amb = 0u; amb = 0u;
+                }
+            }
+            named_bar_sync(ST_BAR_GEN, ST_GEN_THREADS);   // the exchange buffers may be rewritten
+        };
+
+        if (my_tiles > 0) named_bar_arrive(ST_BAR_ACC, ST_ALL);   // nothing to read before the very first pass
+        bool pending = false;
+        int pend_ps = 0;
+        float pend_zsq = 0.0f;
+        uint64_t pend_i = 0;
+        // this thread's 64 bytes per cached K-block: four 16-byte words, consecutive rows consecutive (conflict-free); written in the
+        // first pass and read back by the same thread in the later ones, so the cache needs no synchronisation at all
+        uint4* zc = s_zcache + (size_t)part * 4 * 128 + row;
+        for (uint64_t n = 0; n < my_tiles; ++n) {
+            const uint64_t tile = blockIdx.x + (uint64_t)gridDim.x * n;
+            const uint64_t i = tile * TILE_M + (uint64_t)row;
+            const uint64_t path = p.path_offset + i;
+            PhiloxPath rng;
+            if (!SUPPLIED) rng.init((uint32_t)path, (uint32_t)(path >> 32), p.key1);
+            const double* zrow = SUPPLIED ? p.Z + (size_t)i * (size_t)p.N : nullptr;
+            float zsq_cached = 0.0f;   // sum of squares of this thread's normals in the cached K-blocks
+            for (int ps = 0; ps < NPASS; ++ps) {
+                const int KBN = p.pass[ps].kbn, kend = p.pass[ps].kend;
+                float zsq = ps > 0 ? zsq_cached : 0.0f;
+#pragma unroll 1
+                for (int kb = -1; kb < KBN; ++kb, ++zu) {
+                    const uint32_t slot = zu & 1u;
+                    const uint32_t zaddr = lane_addr + slot * ST_ZCOLS + (uint32_t)(8 * part);
+                    uint32_t hv[8], lv[8];
+                    if (kb >= 0) {
+                        const int col0 = KBLOCK * kb + 16 * part;
+                        uint4* zck = zc + (size_t)kb * (ST_ZCACHE_BYTES / 16);
+                        if (SUPPLIED) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                const double zd = (i < p.M && col0 + q < kend) ? __ldg(zrow + col0 + q) : 0.0;
+                                const float zf = (float)zd;
+                                zsq = fmaf(zf, zf, zsq);
+                                // split the fp64 normal itself: hi = rn16(z), lo = rn16(z - hi)
+                                const __half h = __float2half_rn(zf);
+                                const __half l = __float2half_rn((float)(zd - (double)__half2float(h)));
+                                const uint32_t hb = (uint32_t)__half_as_ushort(h), lb = (uint32_t)__half_as_ushort(l);
+                                if (q & 1) { hv[q >> 1] |= hb << 16; lv[q >> 1] |= lb << 16; }
+                                else { hv[q >> 1] = hb; lv[q >> 1] = lb; }
+                            }
+                        } else if (ps > 0 && kb < KCACHE) {
+                            // generated (and counted into zsq_cached) in the first pass
+                            const uint4 h0 = zck[0], h1 = zck[128], l0 = zck[256], l1 = zck[384];
+                            hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w; hv[4] = h1.x; hv[5] = h1.y; hv[6] = h1.z; hv[7] = h1.w;
+                            lv[0] = l0.x; lv[1] = l0.y; lv[2] = l0.z; lv[3] = l0.w; lv[4] = l1.x; lv[5] = l1.y; lv[6] = l1.z; lv[7] = l1.w;
+                        } else {
+                            float z[16];
+                            if (MCR_STREAM_ABLATE & 2) {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) z[q] = __uint_as_float((((uint32_t)path * 747796405u + (uint32_t)(col0 + q) * 2891336453u) >> 9) | 0x3f000000u);
+                            } else if (col0 + 16 <= kend) {
+                                rng.normals_multi<4>((uint32_t)(col0 >> 2), p.key0, p.key1, z);
+                            } else {   // the K-block that holds the pass's last normal column
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) z[q] = 0.0f;
+#pragma unroll
+                                for (int b = 0; b < 4; ++b)
+                                    if (col0 + 4 * b < kend) rng.normals((uint32_t)((col0 >> 2) + b), p.key0, p.key1, z + 4 * b);
+#pragma unroll
+                                for (int q = 0; q < 16; ++q)
+                                    if (col0 + q >= kend) z[q] = 0.0f;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) zsq = fmaf(z[q], z[q], zsq);
+                            split16(z, hv, lv);
+                            if (ps == 0 && kb < KCACHE) {
+                                zck[0] = make_uint4(hv[0], hv[1], hv[2], hv[3]); zck[128] = make_uint4(hv[4], hv[5], hv[6], hv[7]);
+                                zck[256] = make_uint4(lv[0], lv[1], lv[2], lv[3]); zck[384] = make_uint4(lv[4], lv[5], lv[6], lv[7]);
+                                if (kb == KCACHE - 1) zsq_cached = zsq;
+                            }
+                        }
+                    }
+                    // stay within ST_ZSLOTS slots of the tensor core
+                    if (zu >= (uint32_t)ST_ZSLOTS) mbar_wait<64>(&s_zempty[slot], ((zu / ST_ZSLOTS) - 1u) & 1u);
+                    tc_fence_after();
+                    if (kb >= 0) {
+                        tmem_st8(zaddr, hv);
+                        tmem_st8(zaddr + 32u, lv);
+                    } else if (part == 0) {
+                        const uint32_t ones[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // 1.0 in K columns 0 and 1
+                        tmem_st8(zaddr, ones);
+                    }
+                    tmem_store_wait();
+                    tc_fence_before();
+                    named_bar_arrive(ST_BAR_SLOT + slot, ST_ALL);
+                    // the previous pass is read out once this pass's constant slot and first K-block are queued for the tensor core
+                    if (kb == 0 && pending) {
+                        epilogue(pend_ps, pend_zsq, pend_i, pend_ps == NPASS - 1, true);
+                        pending = false;
+                    }
+                }
+                pending = true; pend_ps = ps; pend_zsq = zsq; pend_i = i;
+            }
+        }
+        if (pending) epilogue(pend_ps, pend_zsq, pend_i, true, false);
+        if (part == 0) {
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            sum_s = __reduce_add_sync(0xffffffffu, sum_s);
+            if (lane == 0) { s_cnt[quarter] = cnt; s_sum[quarter] = sum_s; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t c = 0, s = 0;
+        for (int w = 0; w < 4; ++w) { c += s_cnt[w]; s += s_sum[w]; }
+        p.block_partials[2 * (uint64_t)blockIdx.x] = my_tiles ? c : 0;
+        p.block_partials[2 * (uint64_t)blockIdx.x + 1] = my_tiles ? s : 0;
+    }
+    if (warp == ST_MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+static int round16(int v) { return (v + 15) & ~15; }
+
+// passes over row ranges of at most STREAM_WMAX rows: the first pass takes the remainder, so that with a lower-triangular
+// transform (pass p needs the normals of columns [0, last row of p]) the re-generated columns are as few as possible
+int stream_plan(int N, bool lower, StreamPass* pass) {
+    const int rows = round16(N);
+    const int np = (rows + ST_WMAX - 1) / ST_WMAX;
+    if (np > STREAM_MAX_PASSES) return 0;
+    int r0 = 0;
+    for (int q = 0; q < np; ++q) {
+        const int W = q == 0 ? rows - (np - 1) * ST_WMAX : ST_WMAX;
+        pass[q].r0 = r0; pass[q].W = W;
+        pass[q].kend = lower ? std::min(N, r0 + W) : N;
+        pass[q].kbn = (pass[q].kend + tc::KBLOCK - 1) / tc::KBLOCK;
+        r0 += W;
+    }
+    return np;
+}
+
+bool stream_supported(int N) { return N >= 1 && round16(N) <= ST_WMAX * STREAM_MAX_PASSES && N < MCR_MAX_HIST; }
+
+size_t stream_image_bytes(int N, bool lower) {
+    StreamPass ps[STREAM_MAX_PASSES];
+    const int np = stream_plan(N, lower, ps);
+    size_t b = 0;
+    for (int q = 0; q < np; ++q) {
+        b += (size_t)ps[q].W * 128;
+        for (int kb = 0; kb < ps[q].kbn; ++kb) b += 2 * (size_t)(ps[q].W - stream_acol0(ps[q].r0, kb, lower)) * 128;
+    }
+    return b;
+}
+
+double stream_mma_flops(int N, bool lower) {
+    StreamPass ps[STREAM_MAX_PASSES];
+    const int np = stream_plan(N, lower, ps);
+    double f = 0;
+    for (int q = 0; q < np; ++q) {
+        f += 2.0 * 16.0 * ps[q].W;
+        for (int kb = 0; kb < ps[q].kbn; ++kb) f += 3.0 * 2.0 * 64.0 * (ps[q].W - stream_acol0(ps[q].r0, kb, lower));
+    }
+    return f;
+}
+
+int stream_normals_per_trial(int N, bool lower) {
+    StreamPass ps[STREAM_MAX_PASSES];
+    const int np = stream_plan(N, lower, ps);
+    const int cached = np > 1 ? tc::KBLOCK * std::min(ST_KCACHE_MAX, ps[0].kend / tc::KBLOCK) : 0;
+    int s = 0;
+    for (int q = 0; q < np; ++q) s += ps[q].kend - (q > 0 ? cached : 0);
+    return s;
+}
+
+static void put_half(uint8_t* piece, int r, int kk, __half v) { memcpy(piece + tc::operand_offset(0, r, kk), &v, 2); }
+
+// image: per pass the constant pieces, then per K-block the hi pieces and the lo pieces, one piece per chunk of <= 256 active rows
+// (stream_n1), each (rows) x 64 fp16 in the K-major 128-byte-swizzled operand layout; row i carries s_i A_ij (row_scale:
+// tc_row_scale), the constant piece s_i (mu_i + x) as hi (K column 0) and lo (K column 1); padded rows hold zeros and a large
+// positive constant
+void stream_build(int N, bool lower, const double* A, const double* c, uint8_t* image, double* row_scale) {
+    StreamPass ps[STREAM_MAX_PASSES];
+    const int np = stream_plan(N, lower, ps);
+    memset(image, 0, stream_image_bytes(N, lower));
+    for (int i = 0; i < N; ++i) {
+        double mx = std::fabs(c[i]);
+        for (int k = 0; k < N; ++k) mx = std::max(mx, std::fabs(A[(size_t)i * N + k]));
+        row_scale[i] = tc_row_scale(mx);
+    }
+    auto split = [](double v, __half& hi, __half& lo) {
+        hi = __float2half_rn((float)v);
+        lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+    };
+    uint8_t* out = image;
+    for (int q = 0; q < np; ++q) {
+        const int r0 = ps[q].r0, W = ps[q].W;
+        for (int kb = -1; kb < ps[q].kbn; ++kb) {
+            const int a0 = kb < 0 ? 0 : stream_acol0(r0, kb, lower), w = W - a0, n1 = stream_n1(w);
+            // piece of (half, chunk): halves outer, chunks inner, as the kernel consumes them
+            uint8_t* piece[2][2] = {{out, out + (size_t)n1 * 128}, {out + (size_t)w * 128, out + (size_t)(w + n1) * 128}};
+            for (int r = 0; r < w; ++r) {
+                const int i = r0 + a0 + r, ch = r >= n1 ? 1 : 0, rl = r - (ch ? n1 : 0);
+                __half hi, lo;
+                if (kb < 0) {
+                    split(i < N ? c[i] * row_scale[i] : TC_PAD_ROW, hi, lo);
+                    put_half(piece[0][ch], rl, 0, hi);
+                    put_half(piece[0][ch], rl, 1, lo);
+                    continue;
+                }
+                if (i >= N) break;
+                for (int kk = 0; kk < tc::KBLOCK; ++kk) {
+                    const int j = tc::KBLOCK * kb + kk;
+                    if (j >= ps[q].kend) break;
+                    split(A[(size_t)i * N + j] * row_scale[i], hi, lo);
+                    put_half(piece[0][ch], rl, kk, hi);
+                    put_half(piece[1][ch], rl, kk, lo);
+                }
+            }
+            out += (size_t)w * 128 * (kb < 0 ? 1 : 2);
+        }
+    }
+}
+
+int stream_grid(uint64_t M, int num_sms) {
+    const uint64_t tiles = (M + tc::TILE_M - 1) / tc::TILE_M;
+    return (int)std::min<uint64_t>((uint64_t)num_sms, tiles ? tiles : 1);
+}
+
+cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
+    StreamParams p{};
+    p.M = l.M; p.path_offset = l.path_offset; p.key0 = l.key0; p.key1 = l.key1;
+    p.N = l.N; p.k = l.k; p.lower = l.lower;
+    p.npass = stream_plan(l.N, l.lower != 0, p.pass);
+    if (p.npass <= 0) return cudaErrorInvalidValue;
+    for (int q = 0; q < p.npass; ++q) {
+        p.delta_rel[q] = (float)l.delta_rel[q];
+        p.delta_abs[q] = (float)l.delta_abs[q];
+        // upper bound of the band over all trials: |z_j| < 7 (Box-Muller on 32-bit uniforms); supplied normals: no such bound
+        p.thr_max[q] = l.d_Z ? 3.0e38f : p.delta_rel[q] * 7.0f * sqrtf((float)p.pass[q].kend) * 1.001f + p.delta_abs[q];
+    }
+    p.image = reinterpret_cast<const uint8_t*>(l.d_image); p.Z = l.d_Z;
+    p.S_out = l.S_out; p.flag_list = l.flag_list; p.flag_count = l.flag_count; p.flag_cap = l.flag_cap;
+    p.pair_list = l.pair_list; p.pair_count = l.pair_count; p.pair_cap = l.pair_cap; p.block_partials = l.block_partials;
+    // K-blocks of normals that lie entirely inside the first pass are kept in shared memory for the later passes; the ring of
+    // transform pieces gets the rest of 6 x 32 KB
+    p.kcache = (p.npass > 1 && !l.d_Z) ? std::min(ST_KCACHE_MAX, p.pass[0].kend / tc::KBLOCK) : 0;
+    p.ring = ST_RING_MAX - p.kcache;
+    const size_t smem = (size_t)p.ring * ST_PIECE_MAX + (size_t)p.kcache * ST_ZCACHE_BYTES + 1024;
+    const int grid = stream_grid(l.M, num_sms);
+    cudaError_t e;
+    if (l.d_Z) {
+        e = cudaFuncSetAttribute(tc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        tc_stream_kernel<true><<<grid, ST_THREADS, smem, s>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(tc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        tc_stream_kernel<false><<<grid, ST_THREADS, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace mcr

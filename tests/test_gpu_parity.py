@@ -65,7 +65,7 @@ def test_normals_close_to_libm_box_muller_and_standard(engine, oracle):
 
 # ---------------------------------------------------------------- identical normals
 @pytest.mark.parametrize("name", ["pyref_n15.npz", "pyref_n25.npz"])
-@pytest.mark.parametrize("kernel", [api.KERNEL_FFMA, api.KERNEL_EXACT])
+@pytest.mark.parametrize("kernel", [api.KERNEL_FFMA, api.KERNEL_EXACT, api.KERNEL_TENSOR])
 def test_golden_python_reference_bit_exact(engine, name, kernel):
     g = np.load(GOLD / name)
     engine.upload_sigma(g["mu"], g["Sigma"], api.TRANSFORM_LOWER)
@@ -74,7 +74,7 @@ def test_golden_python_reference_bit_exact(engine, name, kernel):
     assert r.count == int(g["count"]) and r.sum_S == int(g["S_values"].sum())
     assert (r.P_hat, r.std_error, r.ci_lower, r.ci_upper) == \
         (float(g["P_hat"]), float(g["std_error"]), float(g["ci_lower"]), float(g["ci_upper"]))
-    assert r.kernel == ("ffma" if kernel == api.KERNEL_FFMA else "exact")
+    assert r.kernel == {api.KERNEL_FFMA: "ffma", api.KERNEL_EXACT: "exact", api.KERNEL_TENSOR: "tensor"}[kernel]
 
 
 @pytest.mark.parametrize("N,mode,M", [(15, api.TRANSFORM_GSL_FULL, 200000), (15, api.TRANSFORM_LOWER, 100000),
@@ -87,11 +87,14 @@ def test_c_serial_stream_bit_exact(engine, oracle, N, mode, M):
     A = engine.upload_sigma(mu, Sigma, mode)
     np.testing.assert_array_equal(A, oracle.transform(Sigma, mode))
     ro = oracle.run_mt19937(A, mu, k, x, M, 67, want_Z=True)
-    for kernel in (api.KERNEL_FFMA, api.KERNEL_EXACT):
+    # the tensor path too (north-star check 1: identical pre-generated normals fed through the interface): the streamed
+    # tcgen05 kernel reads the caller's fp64 normals from HBM in place of its Philox generator
+    for kernel in (api.KERNEL_FFMA, api.KERNEL_TENSOR, api.KERNEL_EXACT):
         r = engine.run_with_normals(ro["Z"], x, k, kernel=kernel)
         np.testing.assert_array_equal(r.S_values, ro["S_values"])
         assert (r.count, r.sum_S, r.n_paths) == (ro["count"], ro["sum_S"], M)
         assert (r.P_hat, r.std_error, r.ci_lower, r.ci_upper) == oracle.stats(ro["count"], M)
+        assert r.kernel == {api.KERNEL_FFMA: "ffma", api.KERNEL_EXACT: "exact", api.KERNEL_TENSOR: "tensor"}[kernel]
     assert r.n_rechecked == 0  # exact kernel rechecks nothing
 
 
@@ -378,7 +381,7 @@ def test_tensor_kernel_every_tail_shape(engine, oracle, N):
                                       (300, api.TRANSFORM_GSL_FULL, 6000), (500, api.TRANSFORM_LOWER, 5000),
                                       (600, api.TRANSFORM_LOWER, 5000), (1024, api.TRANSFORM_LOWER, 1500)])
 def test_large_n_row_slab_tensor_kernel_bit_exact(engine, oracle, N, mode, M):
-    """N > 128 (Stoxx600 shape): the row-slab tensor kernel (N <= 256, N > 640) and the single-pass one (257..640),
+    """N > 128 (Stoxx600 shape): the streamed tensor kernel (normals in TMEM, one to three passes over row ranges),
     lower-triangular and dense transforms; still bit-exact."""
     m = synthetic_model(N)
     A = engine.upload_sigma(m.mu, m.Sigma, mode)
@@ -432,7 +435,7 @@ def test_slab_fixup_paths_under_a_wide_band():
         "    print(N, r.n_rechecked)\n"
     ) % str(Path(__file__).resolve().parent.parent / "gpu-montecarlo-risk_b200")
     import os, subprocess, sys
-    for large_n in ("slab", "wide"):   # both kernels for N > 128, at every size (AUTO would pick one per size)
+    for large_n in ("stream", "slab", "wide"):   # the streamed kernel (default) and the two round-1 kernels for N > 128, at every size
         p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MCR_TC_BAND_SCALE="32", MCR_LARGE_N=large_n),
                            capture_output=True, text=True, timeout=600)
         assert p.returncode == 0, (large_n, p.stderr[-2000:])

@@ -73,6 +73,40 @@ def test_rows_of_very_different_magnitude(engine, oracle):
         assert (r.count, r.sum_S) == (ro["count"], ro["sum_S"]), r.kernel
 
 
+@pytest.mark.parametrize("N,mode,M", [(129, api.TRANSFORM_LOWER, 20_000), (144, api.TRANSFORM_GSL_FULL, 12_000), (256, api.TRANSFORM_LOWER, 12_000),
+                                      (383, api.TRANSFORM_LOWER, 8_000), (385, api.TRANSFORM_LOWER, 8_000), (400, api.TRANSFORM_GSL_FULL, 5_000),
+                                      (600, api.TRANSFORM_LOWER, 148 * 128 * 2 + 133), (768, api.TRANSFORM_LOWER, 4_000),
+                                      (1000, api.TRANSFORM_GSL_FULL, 2_500), (1024, api.TRANSFORM_LOWER, 3_000)])
+def test_streamed_kernel_every_pass_shape(engine, oracle, N, mode, M):
+    """mcr_stream.cu: one pass (N <= 384), two (N = 385 is 16 + 384 rows) and three (N > 768) passes, ragged last K-block and
+    last row group, lower-triangular (K-blocks skip the rows above them) and dense transforms, several tiles per CTA plus a
+    ragged one at N = 600.  Per-trial S identical to the fp64 oracle on the dumped normals."""
+    m = synthetic_model(N)
+    A = engine.upload_sigma(m.mu, m.Sigma, mode)
+    Z, _ = engine.dump_normals(M, 19)
+    ro = oracle.run_normals(A, m.mu, m.k, m.x, Z)
+    h = api.simulate_host(m.mu, A, M, 19, m.x, m.k, a_is_lower=(mode == api.TRANSFORM_LOWER), want_S_values=True)
+    assert h.kernel == "tensor" and h.padded_N == (N + 15) // 16 * 16
+    np.testing.assert_array_equal(h.S_values, ro["S_values"])
+    assert (h.count, h.sum_S) == (ro["count"], ro["sum_S"])
+    assert h.n_rechecked < M // 5
+
+
+@pytest.mark.parametrize("N,mode,M", [(160, api.TRANSFORM_LOWER, 6_000), (600, api.TRANSFORM_LOWER, 3_000), (600, api.TRANSFORM_GSL_FULL, 1_500),
+                                      (1024, api.TRANSFORM_LOWER, 1_000)])
+def test_supplied_normals_wide_models(engine, oracle, N, mode, M):
+    """The C-serial model's own normal stream (MT19937 + polar method, seed 67) fed through mcr_run_with_normals to the
+    tensor path at Stoxx600-class sizes (round 1: fp64 kernel only)."""
+    m = synthetic_model(N)
+    A = engine.upload_sigma(m.mu, m.Sigma, mode)
+    ro = oracle.run_mt19937(A, m.mu, m.k, m.x, M, 67, want_Z=True)
+    for kernel in (api.KERNEL_TENSOR, api.KERNEL_AUTO, api.KERNEL_EXACT):
+        r = engine.run_with_normals(ro["Z"], m.x, m.k, kernel=kernel)
+        assert r.kernel == ("exact" if kernel == api.KERNEL_EXACT else "tensor")
+        np.testing.assert_array_equal(r.S_values, ro["S_values"])
+        assert (r.count, r.sum_S, r.n_paths) == (ro["count"], ro["sum_S"], M)
+
+
 @pytest.mark.parametrize("N", [15, 50, 160, 600])
 def test_non_positive_k_counts_every_trial(engine, N):
     """S >= k is a signed comparison in the reference (serial.c:137-141): k <= 0 counts every trial, on every kernel."""

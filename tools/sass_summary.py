@@ -34,7 +34,8 @@ print(f"# SASS opcode counts per kernel of {lib.name} (static instruction counts
 print("# columns: total | " + " ".join(OPS))
 agg = collections.OrderedDict()
 for (mangled, c), name in zip(kernels.items(), names):
-    short = re.sub(r"\(.*", "", name).replace("void ", "").replace("mcr::", "")
+    short = re.sub(r"\((?:unsigned )?(?:int|bool|long)\)", "", name)          # template arguments print as (int)64
+    short = re.sub(r"\(.*", "", short).replace("void ", "").replace("mcr::", "")
     agg[short] = c
 for short, c in sorted(agg.items()):
     cols = " ".join(f"{o}={c[o]}" for o in OPS if c[o])
