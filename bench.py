@@ -482,7 +482,7 @@ def main():
         job.upload()   # back to the headline model for the legs below
 
     # ---- rank-0-only legs (the other ranks wait on the host, GPUs idle)
-    e2e = roof = cpu = gpu_ref = None
+    e2e = roof = cpu = gpu_ref = supplied = None
     launches_per_step = 0
     if rank == 0:
         one = eng.run(M, SEED, model.x, model.k, kernel=kernel_sel)
@@ -546,6 +546,30 @@ def main():
                     "note": "FP32-EQUIVALENT: algorithmic flops F(N)=N^2+3N per simulation over the path kernel's CUDA-event time, against "
                             "the FP32 FFMA peak (the metric BASELINE.json names); no per-trial HBM traffic (normals and returns never "
                             "leave the SM).  `fp32_ffma_kernel` is the same workload on the FP32 pipe proper"}
+        # supplied-normals leg (north star: "HBM GB/s wherever normals are materialised"): the same correlate / threshold / reduce
+        # kernels fed M x N fp64 normals resident in HBM (the layout serial.c:67-69 fills) instead of generating them; 8 N bytes
+        # per trial, inputs far larger than L2.  FFMA2 kernel and streamed tcgen05 kernel.
+        if world == 1 and not args.no_configs:
+            try:
+                Mz = 20_000_000 if N <= 64 else max(1_000_000, int(1.0e9 // N))
+                Z = torch.randn(Mz, N, dtype=torch.float64, device="cuda")
+                supplied = {"M": Mz, "bytes_per_trial": 8 * N, "hbm_peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["source"], "kernels": {}}
+                for kname_, ksel in (("ffma", api.KERNEL_FFMA), ("tensor", api.KERNEL_TENSOR)):
+                    if ksel == api.KERNEL_FFMA and N > 128:
+                        continue
+                    best = None
+                    for _ in range(4):
+                        rz = eng.run_with_normals_device(Z.data_ptr(), Mz, model.x, model.k, kernel=ksel)
+                        best = rz.device_ms if best is None else min(best, rz.device_ms)
+                    gbs = Mz * 8 * N / (best * 1e-3) / 1e9
+                    supplied["kernels"][kname_] = {"device_ms": best, "sims_per_s": Mz / (best * 1e-3), "hbm_gbs": gbs,
+                                                   "frac_of_hbm_peak": gbs / peaks["hbm_gbs"], "count": rz.count, "n_rechecked": rz.n_rechecked}
+                ks = list(supplied["kernels"].values())
+                assert all(k_["count"] == ks[0]["count"] for k_ in ks), "kernels disagree on supplied normals"
+                del Z
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                supplied = {"error": repr(ex)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cpu = cpu_reference_leg(model)
@@ -573,7 +597,7 @@ def main():
             "clocks": clocks.summary(),
             "kernel_ms_per_step": kern_total, "comm_ms_per_step": max(0.0, ms_step - kern_total),
             "e2e": e2e, "gpu_launches": launches_per_step * steps,
-            "roofline": roof, "cpu_baseline": cpu, "gpu_baseline": gpu_ref, "configs": configs,
+            "roofline": roof, "cpu_baseline": cpu, "gpu_baseline": gpu_ref, "supplied_normals": supplied, "configs": configs,
             "result": {"count": res.count, "sum_S": res.sum_S, "P_hat": res.P_hat, "n_rechecked": res.n_rechecked},
         }
         print(json.dumps(line))

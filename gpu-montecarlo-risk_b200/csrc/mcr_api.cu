@@ -207,6 +207,14 @@ int mcr_destroy(mcr_engine* e) {
     cudaFree(e->d_port_acc); cudaFree(e->d_port_hist); cudaFree(e->d_port_hist_sum);
     cudaFree(e->d_hist); cudaFree(e->d_S_tmp); cudaFree(e->d_ext_counts); cudaFree(e->d_ext_sums);
     if (e->h_partials) cudaFreeHost(e->h_partials);
+    cudaFree(e->d_S_part);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(e->d_S_compact[b]);
+        if (e->h_S_compact[b]) cudaFreeHost(e->h_S_compact[b]);
+        if (e->ev_compact[b]) cudaEventDestroy(e->ev_compact[b]);
+        if (e->ev_copied[b]) cudaEventDestroy(e->ev_copied[b]);
+    }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_run_done) cudaEventDestroy(e->ev_run_done);
@@ -378,8 +386,9 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
     // histogram of S: needs the per-trial S of every chunk; use the caller's buffer or a per-chunk scratch one
     const bool want_hist = opt && opt->want_hist;
     bool S_is_scratch = false;
+    const bool accumulate = e->accumulate;   // a later part of a run that mcr_simulate_host enqueues in pieces: add to the outputs
     if (want_hist) {
-        MCR_CUDA(cudaMemsetAsync(e->d_hist, 0, sizeof(unsigned long long) * MCR_MAX_HIST, s));
+        if (!accumulate) MCR_CUDA(cudaMemsetAsync(e->d_hist, 0, sizeof(unsigned long long) * MCR_MAX_HIST, s));
         if (!d_S) {
             const uint64_t need = std::min<uint64_t>(M, CHUNK_PATHS);
             if (e->S_tmp_cap < need) {
@@ -392,9 +401,10 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         }
     }
     e->last_hist = want_hist;
-    e->n_timed = 0;
-
-    MCR_CUDA(cudaMemsetAsync(d_out, 0, sizeof(uint64_t) * MCR_PARTIAL_WORDS, s));
+    if (!accumulate) {
+        e->n_timed = 0;
+        MCR_CUDA(cudaMemsetAsync(d_out, 0, sizeof(uint64_t) * MCR_PARTIAL_WORDS, s));
+    }
 
     const FfmaVariant* var = plan.variant >= 0 ? &registry().v[plan.variant] : nullptr;
     int grid_full = 0;
@@ -481,9 +491,11 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             tl.hist_width = (16.0 * sd > 0 ? 16.0 * sd : 1.0) / MCR_PORTFOLIO_BINS;
             tl.port_acc = e->d_port_acc; tl.port_hist = e->d_port_hist; tl.port_hist_sum = e->d_port_hist_sum;
             e->port_hist_lo = tl.hist_lo; e->port_hist_hi = tl.hist_lo + tl.hist_width * MCR_PORTFOLIO_BINS;
-            MCR_CUDA(cudaMemsetAsync(e->d_port_acc, 0, sizeof(double) * 4, s));
-            MCR_CUDA(cudaMemsetAsync(e->d_port_hist, 0, sizeof(unsigned long long) * MCR_PORTFOLIO_BINS, s));
-            MCR_CUDA(cudaMemsetAsync(e->d_port_hist_sum, 0, sizeof(double) * MCR_PORTFOLIO_BINS, s));
+            if (!accumulate) {
+                MCR_CUDA(cudaMemsetAsync(e->d_port_acc, 0, sizeof(double) * 4, s));
+                MCR_CUDA(cudaMemsetAsync(e->d_port_hist, 0, sizeof(unsigned long long) * MCR_PORTFOLIO_BINS, s));
+                MCR_CUDA(cudaMemsetAsync(e->d_port_hist_sum, 0, sizeof(double) * MCR_PORTFOLIO_BINS, s));
+            }
         }
         const uint64_t image_key = e->gen * 2 + (plan.portfolio ? 1 : 0);
         if (e->tc_gen != image_key || e->tc_x != x || plan.portfolio) {
@@ -815,7 +827,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             ++launches;
         }
     }
-    e->last_kernel = plan.kernel; e->last_NT = plan.NT; e->last_launches = launches; e->last_portfolio = plan.portfolio;
+    e->last_kernel = plan.kernel; e->last_NT = plan.NT; e->last_launches = (accumulate ? e->last_launches : 0) + launches; e->last_portfolio = plan.portfolio;
     e->last_mma_flops = mma_flops;
     MCR_CUDA(cudaEventRecord(e->ev_run_done, s));
     e->run_pending = true;

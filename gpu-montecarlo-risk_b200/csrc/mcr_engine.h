@@ -29,6 +29,7 @@ struct mcr_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_run_done = nullptr;   // recorded at the end of every enqueued run: the next run (any stream) waits for it
     bool run_pending = false;
+    bool accumulate = false;   // set by mcr_simulate_host between the parts of one run: the next enqueue_run adds to the outputs instead of zeroing them
     cudaEvent_t evk[2 * mcr::MAX_TIMED_CHUNKS] = {};  // (start, stop) around each path-kernel launch of the last run
     int n_timed = 0;
     // model
@@ -94,6 +95,14 @@ struct mcr_engine {
     int32_t* d_S_tmp = nullptr;
     uint64_t S_tmp_cap = 0;
     bool last_hist = false;
+    // S_values streaming (mcr_simulate_host, want_S_values): per-part int32 scratch, two compact device buffers, two pinned host
+    // buffers, a copy stream and the events that order them
+    int32_t* d_S_part = nullptr;
+    uint8_t* d_S_compact[2] = {nullptr, nullptr};
+    uint8_t* h_S_compact[2] = {nullptr, nullptr};
+    uint64_t S_part_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_compact[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     // extension partials in the mcr_run_async_ext layout (mcr_simulate_host; allocated on first use)
     uint64_t* d_ext_counts = nullptr;
     double* d_ext_sums = nullptr;

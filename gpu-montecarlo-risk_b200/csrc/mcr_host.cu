@@ -17,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace mcr {
@@ -77,6 +78,64 @@ static bool same_model(const mcr_engine* e, const mcr_host_request* r) {
            memcmp(e->A.data(), r->A, sizeof(double) * (size_t)r->N * r->N) == 0;
 }
 
+// ---- S_values on demand: compact on the device, streamed, widened on the host ---------------
+// The reference's models return S (an int per trial, src/model_interface.h:12; monte_carlos_cuda.cu:138-139 copies M ints back
+// in one piece after the kernel).  Here a run that wants S_values is enqueued in parts of S_PART trials: the path kernels write
+// the part's S into an int32 scratch, a small kernel narrows it to one byte per trial (two when N > 255) into one of two
+// compact buffers, a copy stream moves that into pinned host memory while the next part is being simulated, and host threads
+// widen it into the caller's int array.  PCIe carries 1 byte per trial instead of 4, nothing is copied into pageable memory by
+// the driver, and only the last part's copy and widening are not hidden behind the kernels.
+constexpr uint64_t S_PART = 1ull << 23;
+
+template <typename T>
+__global__ void __launch_bounds__(256) narrow_S_kernel(const int32_t* __restrict__ in, T* __restrict__ out, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            const int4 v = *reinterpret_cast<const int4*>(in + i);
+            if (sizeof(T) == 1) *reinterpret_cast<uchar4*>(out + i) = make_uchar4((unsigned char)v.x, (unsigned char)v.y, (unsigned char)v.z, (unsigned char)v.w);
+            else *reinterpret_cast<ushort4*>(out + i) = make_ushort4((unsigned short)v.x, (unsigned short)v.y, (unsigned short)v.z, (unsigned short)v.w);
+        } else {
+            for (uint64_t j = i; j < n; ++j) out[j] = (T)in[j];
+        }
+    }
+}
+
+static int ensure_S_stream(mcr_engine* e, uint64_t part) {
+    if (e->S_part_cap >= part) return 0;
+    cudaFree(e->d_S_part); e->d_S_part = nullptr;
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(e->d_S_compact[b]); e->d_S_compact[b] = nullptr;
+        if (e->h_S_compact[b]) cudaFreeHost(e->h_S_compact[b]);
+        e->h_S_compact[b] = nullptr;
+    }
+    e->S_part_cap = 0;
+    MCR_CUDA(cudaMalloc(&e->d_S_part, sizeof(int32_t) * part));
+    for (int b = 0; b < 2; ++b) {
+        MCR_CUDA(cudaMalloc(&e->d_S_compact[b], 2 * part));
+        MCR_CUDA(cudaHostAlloc(&e->h_S_compact[b], 2 * part, cudaHostAllocPortable));
+        if (!e->ev_compact[b]) MCR_CUDA(cudaEventCreateWithFlags(&e->ev_compact[b], cudaEventDisableTiming));
+        if (!e->ev_copied[b]) MCR_CUDA(cudaEventCreateWithFlags(&e->ev_copied[b], cudaEventDisableTiming));
+    }
+    if (!e->copy_stream) MCR_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    e->S_part_cap = part;
+    return 0;
+}
+
+// compact host buffer -> the caller's int array, on a few host threads (the destination is pageable memory the size of 4 M bytes)
+template <typename T>
+static void widen_S(const T* src, int32_t* dst, uint64_t n) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::min<uint64_t>(std::min(8u, hw), std::max<uint64_t>(1, n >> 18));
+    auto work = [=](uint64_t a, uint64_t b) { for (uint64_t i = a; i < b; ++i) dst[i] = (int32_t)src[i]; };
+    if (nt <= 1) { work(0, n); return; }
+    std::vector<std::thread> th;
+    const uint64_t per = (n + nt - 1) / nt;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, std::min(n, t * per), std::min(n, (t + 1) * per));
+    work(0, std::min(n, per));
+    for (auto& t : th) t.join();
+}
+
 }  // namespace mcr
 
 using namespace mcr;
@@ -94,7 +153,6 @@ extern "C" int mcr_simulate_host(const mcr_host_request* req, mcr_result* out) {
         return fail("mcr_simulate_host: asked for devices %d..%d but %d are visible", req->first_device, req->first_device + n - 1, have);
 
     std::vector<mcr_engine*> eng(n, nullptr);
-    std::vector<int32_t*> dS(n, nullptr);
     std::vector<uint64_t> m(n), off(n);
     uint64_t acc = 0;
     for (int g = 0; g < n; ++g) {
@@ -104,7 +162,7 @@ extern "C" int mcr_simulate_host(const mcr_host_request* req, mcr_result* out) {
     }
     int rc = 0;
     const bool want_ext = req->opt.want_hist || req->opt.want_portfolio;
-    auto cleanup = [&]() { for (int g = 0; g < n; ++g) if (dS[g]) { cudaSetDevice(eng[g]->device); cudaFree(dS[g]); } };
+    const bool narrow8 = req->N <= 255;   // S <= N fits a byte
 
     for (int g = 0; g < n && !rc; ++g) {
         if (get_engine(req->first_device + g, &eng[g])) { rc = -1; break; }
@@ -122,28 +180,85 @@ extern "C" int mcr_simulate_host(const mcr_host_request* req, mcr_result* out) {
         }
     }
     // enqueue every shard, then the all-reduce, then wait
+    auto enqueue_ext = [&](mcr_engine* e) -> int {
+        // extension partials of this shard in the all-reducible layout of mcr_run_async_ext
+        if (!e->d_ext_counts && (cudaMalloc(&e->d_ext_counts, sizeof(uint64_t) * MCR_EXT_COUNT_WORDS) != cudaSuccess ||
+                                 cudaMalloc(&e->d_ext_sums, sizeof(double) * MCR_EXT_SUM_WORDS) != cudaSuccess))
+            return fail("extension partial buffers: allocation failed on device %d", e->device);
+        return enqueue_gather_ext(e, e->d_ext_counts, e->d_ext_sums, e->stream);
+    };
     for (int g = 0; g < n && !rc; ++g) {
-        mcr_engine* e = eng[g];
-        cudaSetDevice(e->device);
-        mcr_run_options o = req->opt;
-        o.struct_size = sizeof(o);
-        o.d_S_values = nullptr;
-        if (req->want_S_values && m[g]) {
-            if (cudaMalloc(&dS[g], sizeof(int32_t) * m[g]) != cudaSuccess) { rc = fail("S_values allocation (%llu ints) failed on device %d", (unsigned long long)m[g], e->device); break; }
-            o.d_S_values = dS[g];
-        }
-        cudaEventRecord(e->ev0, e->stream);
-        rc = enqueue_run(e, m[g], off[g], req->seed, req->x, req->k, &o, nullptr, e->d_partials, e->stream);
-        if (!rc && want_ext) {
-            // extension partials of this shard in the all-reducible layout of mcr_run_async_ext
-            if (!e->d_ext_counts && (cudaMalloc(&e->d_ext_counts, sizeof(uint64_t) * MCR_EXT_COUNT_WORDS) != cudaSuccess ||
-                                     cudaMalloc(&e->d_ext_sums, sizeof(double) * MCR_EXT_SUM_WORDS) != cudaSuccess)) {
-                rc = fail("extension partial buffers: allocation failed on device %d", e->device);
-                break;
-            }
-            rc = enqueue_gather_ext(e, e->d_ext_counts, e->d_ext_sums, e->stream);
-        }
+        cudaSetDevice(eng[g]->device);
+        cudaEventRecord(eng[g]->ev0, eng[g]->stream);
+        eng[g]->accumulate = false;
     }
+    if (!req->want_S_values) {
+        for (int g = 0; g < n && !rc; ++g) {
+            mcr_engine* e = eng[g];
+            cudaSetDevice(e->device);
+            mcr_run_options o = req->opt;
+            o.struct_size = sizeof(o);
+            o.d_S_values = nullptr;
+            rc = enqueue_run(e, m[g], off[g], req->seed, req->x, req->k, &o, nullptr, e->d_partials, e->stream);
+            if (!rc && want_ext) rc = enqueue_ext(e);
+        }
+    } else {
+        // S_values: the shard of every device in parts of S_PART trials; part j is narrowed and copied out while part j + 1 runs,
+        // and widened into the caller's array by this thread (and helpers) while the GPUs work on
+        uint64_t parts = 0;
+        for (int g = 0; g < n; ++g) parts = std::max<uint64_t>(parts, (m[g] + S_PART - 1) / S_PART);
+        for (int g = 0; g < n && !rc; ++g) {
+            cudaSetDevice(eng[g]->device);
+            rc = ensure_S_stream(eng[g], S_PART);
+        }
+        auto widen_part = [&](uint64_t j) -> int {   // wait for part j of every device and widen it
+            for (int g = 0; g < n; ++g) {
+                const uint64_t a = j * S_PART;
+                if (a >= m[g]) continue;
+                const uint64_t cnt = std::min<uint64_t>(S_PART, m[g] - a);
+                mcr_engine* e = eng[g];
+                cudaSetDevice(e->device);
+                if (cudaEventSynchronize(e->ev_copied[j & 1]) != cudaSuccess) return fail("device %d: S_values copy failed: %s", e->device, cudaGetErrorString(cudaGetLastError()));
+                if (narrow8) widen_S(reinterpret_cast<const uint8_t*>(e->h_S_compact[j & 1]), req->S_values_out + off[g] + a, cnt);
+                else widen_S(reinterpret_cast<const uint16_t*>(e->h_S_compact[j & 1]), req->S_values_out + off[g] + a, cnt);
+            }
+            return 0;
+        };
+        for (uint64_t j = 0; j < std::max<uint64_t>(parts, 1) && !rc; ++j) {
+            for (int g = 0; g < n && !rc; ++g) {
+                mcr_engine* e = eng[g];
+                const uint64_t a = j * S_PART;
+                if (a >= m[g] && !(j == 0)) continue;   // (an empty shard still runs once, so that its partial words are zeroed)
+                const uint64_t cnt = a < m[g] ? std::min<uint64_t>(S_PART, m[g] - a) : 0;
+                cudaSetDevice(e->device);
+                mcr_run_options o = req->opt;
+                o.struct_size = sizeof(o);
+                o.d_S_values = e->d_S_part;
+                rc = enqueue_run(e, cnt, off[g] + a, req->seed, req->x, req->k, &o, nullptr, e->d_partials, e->stream);
+                e->accumulate = true;
+                if (rc || cnt == 0) continue;
+                const int b = (int)(j & 1);
+                if (j >= 2) cudaStreamWaitEvent(e->stream, e->ev_copied[b], 0);   // the compact buffer's previous content has left the device
+                const int grid = (int)std::min<uint64_t>((uint64_t)e->num_sms * 8, (cnt / 4 + 255) / 256 + 1);
+                if (narrow8) narrow_S_kernel<uint8_t><<<grid, 256, 0, e->stream>>>(e->d_S_part, e->d_S_compact[b], cnt);
+                else narrow_S_kernel<uint16_t><<<grid, 256, 0, e->stream>>>(e->d_S_part, reinterpret_cast<uint16_t*>(e->d_S_compact[b]), cnt);
+                cudaEventRecord(e->ev_compact[b], e->stream);
+                cudaStreamWaitEvent(e->copy_stream, e->ev_compact[b], 0);
+                cudaMemcpyAsync(e->h_S_compact[b], e->d_S_compact[b], cnt * (narrow8 ? 1 : 2), cudaMemcpyDeviceToHost, e->copy_stream);
+                cudaEventRecord(e->ev_copied[b], e->copy_stream);
+                ++e->last_launches;
+                if (cudaGetLastError() != cudaSuccess) rc = fail("device %d: S_values streaming failed", e->device);
+            }
+            if (!rc && j >= 1) rc = widen_part(j - 1);
+        }
+        for (int g = 0; g < n && !rc; ++g) {
+            eng[g]->accumulate = false;
+            cudaSetDevice(eng[g]->device);
+            if (want_ext) rc = enqueue_ext(eng[g]);
+        }
+        if (!rc && parts >= 1) rc = widen_part(parts - 1);
+    }
+    for (int g = 0; g < n; ++g) if (eng[g]) eng[g]->accumulate = false;
     if (n > 1 && !rc) {
         std::vector<ncclComm_t>& comms = g_comms[{req->first_device, n}];
         g_nccl.GroupStart();
@@ -167,7 +282,6 @@ extern "C" int mcr_simulate_host(const mcr_host_request* req, mcr_result* out) {
         cudaSetDevice(e->device);
         cudaEventRecord(e->ev1, e->stream);
         cudaMemcpyAsync(e->h_partials, e->d_partials, sizeof(uint64_t) * MCR_PARTIAL_WORDS, cudaMemcpyDeviceToHost, e->stream);
-        if (dS[g]) cudaMemcpyAsync(req->S_values_out + off[g], dS[g], sizeof(int32_t) * m[g], cudaMemcpyDeviceToHost, e->stream);
         if (want_ext && g == 0) {   // after the all-reduce every device holds the totals
             e->h_ext_counts.resize(MCR_EXT_COUNT_WORDS);
             e->h_ext_sums.resize(MCR_EXT_SUM_WORDS);
@@ -195,6 +309,5 @@ extern "C" int mcr_simulate_host(const mcr_host_request* req, mcr_result* out) {
         out->launches = launches;
         if (!rc && out->n_paths != req->M) rc = fail("internal: reduced %llu paths, expected %llu", (unsigned long long)out->n_paths, (unsigned long long)req->M);
     }
-    cleanup();
     return rc;
 }

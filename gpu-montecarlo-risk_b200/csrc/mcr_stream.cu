@@ -34,6 +34,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace mcr {
@@ -68,6 +69,7 @@ static_assert(ST_RING_MAX * ST_PIECE_MAX + 1024 <= 220 * 1024 && (ST_RING_MAX - 
 struct StreamParams {
     uint64_t M, path_offset;
     uint32_t key0, key1;
+    PhiloxKeys keys;           // the round keys of (key0, key1): constant-bank operands of the generator
     int32_t N, k, lower, npass;
     int32_t ring;              // ring slots in use
     int32_t kcache;            // K-blocks 0 .. kcache - 1 of a tile's normals are kept in shared memory after the first pass
@@ -118,6 +120,22 @@ __device__ __forceinline__ void bulk_g2s_st(uint32_t dst_smem, const void* src, 
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// the same copy delivered to the same shared-memory offset (and signalled on the mbarrier at the same offset) of every CTA in cta_mask
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 }  // namespace tc
 
 // 16 normals -> 8 + 8 packed fp16 pairs (hi, lo); same split as store_chunk: hi = rn16(z), lo = rn16(z - hi)
@@ -146,20 +164,28 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
 
     // the warp index through a shuffle: warp-uniform for the compiler (role loops keep their state in uniform registers)
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    // CTA pairs (clusters of 2, the two SMs of a TPC) share the transform stream: each CTA fetches every other piece and multicasts
+    // it into both rings.  At full tensor rate one SM consumes ~43 bytes of transform per clock, which is the whole chip's L2
+    // bandwidth divided by 148 (profiles/r02_stream_kernel_development.log): unshared, the L2 stream and the MMAs take turns.
+    const uint32_t csz = cluster_nctarank(), crank = cluster_ctarank();
+    const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
     if (tid == 0) {
         for (int b = 0; b < ST_ZSLOTS; ++b) mbar_init(&s_zempty[b], 1);
-        for (int b = 0; b < ST_RING_MAX; ++b) { mbar_init(&s_bfull[b], 1); mbar_init(&s_bempty[b], 1); }
+        for (int b = 0; b < ST_RING_MAX; ++b) { mbar_init(&s_bfull[b], 1); mbar_init(&s_bempty[b], csz); }
         mbar_init(&s_done, 1);
     }
     if (warp == ST_MMA_WARP) tmem_alloc(&s_tmem, 512);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (csz > 1) cluster_sync_all();   // the partner's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
 
+    // every CTA runs the same number of tiles (a pair must consume the shared stream in step); tiles past the end are ghosts
+    // whose trials (i >= M) are generated and multiplied like any other but never counted
     const uint64_t n_tiles = (p.M + TILE_M - 1) / TILE_M;
-    const uint64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint64_t my_tiles = (n_tiles + gridDim.x - 1) / gridDim.x;
     const int NPASS = p.npass, LOWER = p.lower;
 
     if (warp == ST_MMA_WARP) {
@@ -183,7 +209,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                             const uint32_t d = c ? d1 + (uint32_t)n1 : d1;
                             const uint32_t id = make_idesc(c ? n2 : n1);
                             const bool last = half == (kb < 0 ? 0 : 1) && c == (n2 > 0 ? 1 : 0);
-                            mbar_wait(&s_bfull[rs], rphase);
+                            mbar_wait<20>(&s_bfull[rs], rphase);
                             if (elect_one()) {
                                 tc_fence_after();
                                 const uint64_t b = make_desc(smem_u32(s_ring + rs * ST_PIECE_MAX));
@@ -200,7 +226,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                                         for (int ks = 0; ks < KBLOCK / 16; ++ks) umma_f16_ts(d, a_hi + 8 * ks, b + 2 * ks, id, 1u);
                                     }
                                 }
-                                umma_commit(&s_bempty[rs]);
+                                if (csz > 1) umma_commit_multicast(&s_bempty[rs], cmask);   // both rings' slot rs: one more consumer done
+                                else umma_commit(&s_bempty[rs]);
                                 if (last) {
                                     umma_commit(&s_zempty[slot]);
                                     if (kb == KBN - 1) umma_commit(&s_done);
@@ -226,12 +253,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                         for (int half = 0; half < (kb < 0 ? 1 : 2); ++half)
                             for (int c = 0; c < (n2 > 0 ? 2 : 1); ++c, ++piece) {
                                 const uint32_t bytes = (uint32_t)(c ? n2 : n1) * 128u;
-                                if (piece >= (uint32_t)RING) mbar_wait(&s_bempty[rs], rphase ^ 1u);
+                                // slot rs has been consumed by every CTA of the pair (their commits arrive on both copies of s_bempty)
+                                if (piece >= (uint32_t)RING) mbar_wait<20>(&s_bempty[rs], rphase ^ 1u);
                                 if ((MCR_STREAM_ABLATE & 1) && piece >= (uint32_t)RING) {
                                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_bfull[rs])) : "memory");
                                 } else {
-                                    mbar_expect_tx_st(&s_bfull[rs], bytes);
-                                    bulk_g2s_st(smem_u32(s_ring + rs * ST_PIECE_MAX), src, bytes, &s_bfull[rs]);
+                                    mbar_expect_tx_st(&s_bfull[rs], bytes);   // this CTA's copy, whoever fetches it
+                                    if (csz == 1) bulk_g2s_st(smem_u32(s_ring + rs * ST_PIECE_MAX), src, bytes, &s_bfull[rs]);
+                                    else if ((piece & 1u) == crank) bulk_g2s_multicast(smem_u32(s_ring + rs * ST_PIECE_MAX), src, bytes, &s_bfull[rs], cmask);
                                 }
                                 src += bytes;
                                 if (++rs == (uint32_t)RING) { rs = 0; rphase ^= 1u; }
@@ -250,45 +279,60 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
         // state of the trial in this thread's row across the passes of a tile (kept by the part-0 thread of the row)
         uint32_t S_tot = 0, n_amb = 0, amb = 0;
 
-        // Read one pass out of the accumulators: per 32-column group (dealt round-robin to the four parts of the row) the sign
-        // bits and, where anything can be inside the band, the two smallest keys; combined per row in shared memory.
-        auto epilogue = [&](int ps, float zsq, uint64_t i, bool last_of_tile, bool more_work) {
-            mbar_wait<64>(&s_done, done_parity);
-            done_parity ^= 1u;
-            tc_fence_after();
-            const int W = p.pass[ps].W, r0 = p.pass[ps].r0;
+        // Read-out of the current pass, per thread: the 32-column groups g = part, part + 4, ... of the row (dealt round-robin to
+        // its four threads).  c_next = first column of this thread's next group; S_pass / k1 <= k2 = the sign bits counted and the
+        // two smallest keys (|accumulator|, column, sign) seen so far.
+        uint32_t S_pass = 0, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+        int c_next = 32 * part;
+
+        // read this thread's groups that end at or below column `upto` (everything left with final_part)
+        auto read_columns = [&](int ps, int upto, bool final_part) {
+            const int W = p.pass[ps].W;
             const float thr_max = p.thr_max[ps];
-            uint32_t S = 0, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
 #pragma unroll 1
-            for (int c0 = 32 * part; c0 < W; c0 += 32 * ST_PARTS) {
+            while (final_part ? c_next < W : c_next + 32 <= upto) {
                 uint32_t v[32];
-                tmem_ld32(lane_addr + (uint32_t)(ST_ACC_COL + c0), v);
+                tmem_ld32(lane_addr + (uint32_t)(ST_ACC_COL + c_next), v);
                 tmem_ld_wait();
-                const int valid = W - c0;    // a multiple of 16: the last group of a pass may hold only 16 columns
+                const int valid = W - c_next;    // a multiple of 16: the last group of a pass may hold only 16 columns
                 float m = 3.0e38f;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
+                for (int c = 0; c < 32; c += 2) {
                     if (c < 16 || valid > 16) {
-                        S += v[c] >> 31;
-                        m = fminf(m, fabsf(__uint_as_float(v[c])));
+                        S_pass += (v[c] >> 31) + (v[c + 1] >> 31);
+                        m = fminf(m, fminf(fabsf(__uint_as_float(v[c])), fabsf(__uint_as_float(v[c + 1]))));
                     }
                 }
                 if (m < thr_max) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         if (c < 16 || valid > 16) {
-                            const uint32_t key = (__funnelshift_l(v[c], v[c], 1) & (ST_KEY_MASK | 1u)) | ((uint32_t)(c0 + c) << 1);
+                            const uint32_t key = (__funnelshift_l(v[c], v[c], 1) & (ST_KEY_MASK | 1u)) | ((uint32_t)(c_next + c) << 1);
                             k2 = min(k2, max(k1, key));
                             k1 = min(k1, key);
                         }
                     }
                 }
+                c_next += 32 * ST_PARTS;
             }
+        };
+
+        // End of a pass: the rest of its columns, then the four threads of a row combine in shared memory and the part-0 thread
+        // decides about the near-threshold decisions.
+        auto epilogue = [&](int ps, float zsq, uint64_t i, bool last_of_tile, bool more_work) {
+            mbar_wait<64>(&s_done, done_parity);
+            done_parity ^= 1u;
+            tc_fence_after();
+            const int r0 = p.pass[ps].r0;
+            read_columns(ps, p.pass[ps].W, true);
+            uint32_t S = S_pass;
+            const uint32_t k1_ = k1, k2_ = k2;
+            S_pass = 0u; k1 = 0xFFFFFFFFu; k2 = 0xFFFFFFFFu; c_next = 32 * part;
             tc_fence_before();
             if (more_work) named_bar_arrive(ST_BAR_ACC, ST_ALL);   // the MMA warp may overwrite the accumulators (next pass)
             s_part_S[part][row] = S;
-            s_part_k1[part][row] = k1;
-            s_part_k2[part][row] = k2;
+            s_part_k1[part][row] = k1_;
+            s_part_k2[part][row] = k2_;
             s_part_zsq[part][row] = zsq;
             named_bar_sync(ST_BAR_GEN, ST_GEN_THREADS);
             if (part == 0) {
@@ -387,19 +431,21 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
 #pragma unroll
                                 for (int q = 0; q < 16; ++q) z[q] = __uint_as_float((((uint32_t)path * 747796405u + (uint32_t)(col0 + q) * 2891336453u) >> 9) | 0x3f000000u);
                             } else if (col0 + 16 <= kend) {
-                                rng.normals_multi<4>((uint32_t)(col0 >> 2), p.key0, p.key1, z);
+                                rng.normals_multi<4>((uint32_t)(col0 >> 2), p.keys, z);
                             } else {   // the K-block that holds the pass's last normal column
 #pragma unroll
                                 for (int q = 0; q < 16; ++q) z[q] = 0.0f;
 #pragma unroll
                                 for (int b = 0; b < 4; ++b)
-                                    if (col0 + 4 * b < kend) rng.normals((uint32_t)((col0 >> 2) + b), p.key0, p.key1, z + 4 * b);
+                                    if (col0 + 4 * b < kend) rng.normals((uint32_t)((col0 >> 2) + b), p.keys, z + 4 * b);
 #pragma unroll
                                 for (int q = 0; q < 16; ++q)
                                     if (col0 + q >= kend) z[q] = 0.0f;
                             }
+                            float2 acc2 = make_float2(zsq, 0.0f);
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) zsq = fmaf(z[q], z[q], zsq);
+                            for (int q = 0; q < 8; ++q) acc2 = __ffma2_rn(make_float2(z[2 * q], z[2 * q + 1]), make_float2(z[2 * q], z[2 * q + 1]), acc2);
+                            zsq = acc2.x + acc2.y;
                             split16(z, hv, lv);
                             if (ps == 0 && kb < KCACHE) {
                                 zck[0] = make_uint4(hv[0], hv[1], hv[2], hv[3]); zck[128] = make_uint4(hv[4], hv[5], hv[6], hv[7]);
@@ -411,6 +457,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                     // stay within ST_ZSLOTS slots of the tensor core
                     if (zu >= (uint32_t)ST_ZSLOTS) mbar_wait<64>(&s_zempty[slot], ((zu / ST_ZSLOTS) - 1u) & 1u);
                     tc_fence_after();
+                    // The slot is free, so the MMAs of this pass's K-block kb - 2 are complete; with a lower-triangular transform the
+                    // K-blocks after it only touch the rows >= 64 (kb - 1), so the accumulator columns below that are final and are read
+                    // now, while the tensor core works on.  The end of the pass is then left with the last few columns: neither do the
+                    // generators wait long for the tensor core to drain, nor the tensor core for the read-out.  (The previous pass
+                    // is pending until this pass's K-block 0 has been queued: nothing is read early before kb = 2.)
+                    if (LOWER && kb >= 2) read_columns(ps, min(p.pass[ps].W, 64 * (kb - 1) - p.pass[ps].r0), false);
                     if (kb >= 0) {
                         tmem_st8(zaddr, hv);
                         tmem_st8(zaddr + 32u, lv);
@@ -440,6 +492,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
 
     tc_fence_before();
     __syncthreads();
+    if (csz > 1) cluster_sync_all();   // nothing of the partner's is still in flight towards this CTA's shared memory
     if (tid == 0) {
         uint64_t c = 0, s = 0;
         for (int w = 0; w < 4; ++w) { c += s_cnt[w]; s += s_sum[w]; }
@@ -551,9 +604,12 @@ void stream_build(int N, bool lower, const double* A, const double* c, uint8_t* 
     }
 }
 
+// one CTA per SM; an even count (CTA pairs share the transform stream) unless there is a single tile
 int stream_grid(uint64_t M, int num_sms) {
     const uint64_t tiles = (M + tc::TILE_M - 1) / tc::TILE_M;
-    return (int)std::min<uint64_t>((uint64_t)num_sms, tiles ? tiles : 1);
+    int g = (int)std::min<uint64_t>((uint64_t)num_sms, tiles ? tiles : 1);
+    if (g > 1) g &= ~1;
+    return g;
 }
 
 cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
@@ -576,18 +632,26 @@ cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
     p.kcache = (p.npass > 1 && !l.d_Z) ? std::min(ST_KCACHE_MAX, p.pass[0].kend / tc::KBLOCK) : 0;
     p.ring = ST_RING_MAX - p.kcache;
     const size_t smem = (size_t)p.ring * ST_PIECE_MAX + (size_t)p.kcache * ST_ZCACHE_BYTES + 1024;
+    p.keys.set(l.key0, l.key1);
     const int grid = stream_grid(l.M, num_sms);
+    static const int want_cluster = [] { const char* v = getenv("MCR_STREAM_CLUSTER"); return v && *v ? atoi(v) : 2; }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(ST_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (want_cluster == 2 && grid % 2 == 0) ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e;
     if (l.d_Z) {
         e = cudaFuncSetAttribute(tc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        tc_stream_kernel<true><<<grid, ST_THREADS, smem, s>>>(p);
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<true>, p);
     } else {
         e = cudaFuncSetAttribute(tc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        tc_stream_kernel<false><<<grid, ST_THREADS, smem, s>>>(p);
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false>, p);
     }
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace mcr

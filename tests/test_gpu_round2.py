@@ -137,6 +137,27 @@ def test_runs_on_different_streams_are_ordered(engine):
             assert (r.count, r.sum_S) == (w.count, w.sum_S)
 
 
+@pytest.mark.parametrize("N,M", [(50, (2 << 23) + 12_345), (300, (1 << 23) + 777)])
+def test_streamed_S_values_over_several_parts(engine, oracle, N, M):
+    """S_values on demand (reference: MonteCarloResult.S_values, src/model_interface.h:12): the run is enqueued in parts of 2^23
+    trials, each narrowed on the device to one byte per trial (two for N > 255), copied to pinned memory while the next part runs
+    and widened into the caller's int array.  Totals equal the plain run; windows at the part boundaries equal the oracle."""
+    m = synthetic_model(N)
+    A = engine.upload_sigma(m.mu, m.Sigma)
+    plain = engine.run(M, 67, m.x, m.k)
+    h = api.simulate_host(m.mu, A, M, 67, m.x, m.k, a_is_lower=True, want_S_values=True, want_hist=True)
+    assert (h.count, h.sum_S, h.n_paths) == (plain.count, plain.sum_S, M)
+    S = h.S_values
+    assert S.dtype == np.int32 and S.shape == (M,)
+    assert int(S.sum(dtype=np.int64)) == plain.sum_S and int((S >= m.k).sum()) == plain.count
+    np.testing.assert_array_equal(np.bincount(S, minlength=N + 1), h.hist_S)
+    for start in (0, (1 << 23) - 700, (2 << 23) - 700 if M > (2 << 23) else M - 2000, M - 1400):
+        cnt = 1400
+        Z, _ = engine.dump_normals(cnt, 67, path_offset=start)
+        ro = oracle.run_normals(A, m.mu, m.k, m.x, Z)
+        np.testing.assert_array_equal(S[start:start + cnt], ro["S_values"])
+
+
 def test_mma_flops_accounting(engine):
     m = synthetic_model(50)
     engine.upload_sigma(m.mu, m.Sigma)

@@ -14,6 +14,7 @@
 #   tune:<N>:<M>[:libs]   tools/tune.py over devlibs/*/ (or the comma-separated subset)
 #   tuneraw:<N>:<M>[:libs] the same with no_recheck (ablated builds return garbage decisions)
 #   ubench:<name>         tools/<name> (a prebuilt micro-benchmark binary)
+#   env:VAR=VALUE         export a variable for the stages that follow
 #   py:<script>[:ARGS]    python tools/<script> ARGS
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out; O=gpurun_out
@@ -38,6 +39,7 @@ for stage in "$@"; do
     tuneraw)  echo "## (no recheck) N=$a M=$b" >> $S; MCR_TUNE_NORECHECK=1 MCR_TUNE_LIBS=$c timeout 600 python tools/tune.py $a $b >> $S 2>&1; rc=$? ;;
     ubench)   timeout 300 tools/$a > $O/${a}_$tag.log 2>&1; rc=$?; tail -n 40 $O/${a}_$tag.log ;;
     py)       timeout 900 python tools/$a ${b//,/ } > $O/${a%.py}_$tag.log 2>&1; rc=$?; tail -n 30 $O/${a%.py}_$tag.log ;;
+    env)      export "$a"; rc=0 ;;
     *)        echo "unknown stage $stage"; rc=99 ;;
   esac
   echo "$stage rc=$rc" | tee -a $S
