@@ -320,22 +320,24 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
     plan->portfolio = opt && opt->want_portfolio;
     plan->slab = false;
     plan->rows = e->N + (plan->portfolio ? 1 : 0);
-    if (!plan->portfolio && (e->N > tc_max_n() || normals) && (want == MCR_KERNEL_TENSOR || (want == MCR_KERNEL_AUTO && e->N > tc_max_n())) &&
-        stream_supported(e->N)) {
-        // N > 128, and every supplied-normals run that asks for the tensor path: the streamed kernel (mcr_stream.cu).  The two
-        // round-1 kernels stay selectable for A/B runs: MCR_LARGE_N=slab|wide (generated normals only).
+    if (plan->portfolio && normals) return fail("portfolio outputs are not available with supplied normals");
+    if ((plan->rows > tc_max_n() || normals) && (want == MCR_KERNEL_TENSOR || (want == MCR_KERNEL_AUTO && plan->rows > tc_max_n())) &&
+        stream_supported(e->N, plan->portfolio ? 1 : 0)) {
+        // more accumulator rows than the tile kernel holds (N > 128, or N = 128 plus the portfolio row), and every supplied-normals
+        // run that asks for the tensor path: the streamed kernel (mcr_stream.cu).  The two round-1 kernels stay selectable for A/B
+        // runs: MCR_LARGE_N=slab|wide (generated normals, no portfolio outputs).
         static const int forced = [] { const char* v = getenv("MCR_LARGE_N"); return !v ? 0 : !strcmp(v, "slab") ? 1 : !strcmp(v, "wide") ? 2 : 0; }();
         plan->kernel = MCR_KERNEL_TENSOR;
-        if (!normals && e->N > tc_max_n() && forced == 2 && wide_supported(e->N)) { plan->wide = true; plan->NT = 128 * wide_slabs(e->N); }
-        else if (!normals && e->N > tc_max_n() && forced == 1) { plan->slab = true; plan->NT = slab_rows() * slab_count(e->N); }
-        else { plan->stream = true; plan->NT = (e->N + 15) & ~15; }
+        const bool r1_ok = !normals && !plan->portfolio && e->N > tc_max_n();
+        if (r1_ok && forced == 2 && wide_supported(e->N)) { plan->wide = true; plan->NT = 128 * wide_slabs(e->N); }
+        else if (r1_ok && forced == 1) { plan->slab = true; plan->NT = slab_rows() * slab_count(e->N); }
+        else { plan->stream = true; plan->NT = (plan->rows + 15) & ~15; }
         return 0;
     }
     const bool tc_ok = !normals && tc_supported(plan->rows);
     if (plan->portfolio) {
         if (want != MCR_KERNEL_AUTO && want != MCR_KERNEL_TENSOR) return fail("portfolio outputs are produced by the tensor-core kernel only");
-        if (normals) return fail("portfolio outputs are not available with supplied normals");
-        if (!tc_ok) return fail("portfolio outputs need N <= %d (N=%d)", tc_max_n() - 1, e->N);
+        if (!tc_ok) return fail("portfolio outputs: N=%d is outside the tensor kernels' range", e->N);
         plan->kernel = MCR_KERNEL_TENSOR; plan->NT = tc_padded_n(plan->rows);
         return 0;
     }
@@ -386,6 +388,8 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
     // histogram of S: needs the per-trial S of every chunk; use the caller's buffer or a per-chunk scratch one
     const bool want_hist = opt && opt->want_hist;
     bool S_is_scratch = false;
+    // SMs the path kernels may fill: all of them, less the ones the caller keeps free for a collective that runs concurrently
+    const int sms = std::max(2, e->num_sms - ((opt && opt->sm_reserve > 0) ? std::min(opt->sm_reserve, e->num_sms / 2) : 0));
     const bool accumulate = e->accumulate;   // a later part of a run that mcr_simulate_host enqueues in pieces: add to the outputs
     if (want_hist) {
         if (!accumulate) MCR_CUDA(cudaMemsetAsync(e->d_hist, 0, sizeof(unsigned long long) * MCR_MAX_HIST, s));
@@ -452,11 +456,35 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         int bps = 0;
         MCR_CUDA(var->occupancy(128, &bps));
         if (bps < 1) return fail("FFMA kernel NT=%d cannot be resident", plan.NT);
-        grid_full = std::min(e->num_sms * bps, MAX_GRID);
+        grid_full = std::min(sms * bps, MAX_GRID);
         fp.key0 = key0; fp.key1 = key1; fp.k = k; fp.N = N;
         fp.flag_list = e->d_flag_list; fp.flag_count = e->d_flag_count; fp.flag_cap = FLAG_CAP;
         fp.block_partials = e->d_block_partials;
     }
+
+    // portfolio extension: the extra image row (w^T A, then w.mu), the histogram range (w.mu +- 8 sigma_p: a function of the model
+    // and the weights only, so every shard and GPU bins identically), zeroed accumulators
+    auto prepare_portfolio = [&](std::vector<double>& port_row, double& hist_lo, double& hist_width) -> int {
+        port_row.assign(N + 1, 0.0);
+        double var = 0;
+        for (int j = 0; j < N; ++j) {
+            double vj = 0;
+            for (int i = 0; i < N; ++i) vj += e->w[i] * e->A[(size_t)i * N + j];
+            port_row[j] = vj;
+            var += vj * vj;
+        }
+        for (int i = 0; i < N; ++i) port_row[N] += e->w[i] * e->mu[i];
+        const double sd = std::sqrt(var);
+        hist_lo = port_row[N] - 8.0 * sd;
+        hist_width = (16.0 * sd > 0 ? 16.0 * sd : 1.0) / MCR_PORTFOLIO_BINS;
+        e->port_hist_lo = hist_lo; e->port_hist_hi = hist_lo + hist_width * MCR_PORTFOLIO_BINS;
+        if (!accumulate) {
+            MCR_CUDA(cudaMemsetAsync(e->d_port_acc, 0, sizeof(double) * 4, s));
+            MCR_CUDA(cudaMemsetAsync(e->d_port_hist, 0, sizeof(unsigned long long) * MCR_PORTFOLIO_BINS, s));
+            MCR_CUDA(cudaMemsetAsync(e->d_port_hist_sum, 0, sizeof(double) * MCR_PORTFOLIO_BINS, s));
+        }
+        return 0;
+    };
 
     TcLaunch tl{};
     int tc_grid_full = 0;
@@ -475,27 +503,10 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         // portfolio row: P = w.R = w.mu + (w^T A) z rides through the same MMAs as one more output row
         std::vector<double> port_row;
         if (plan.portfolio) {
-            port_row.assign(N + 1, 0.0);
-            double var = 0;
-            for (int j = 0; j < N; ++j) {
-                double vj = 0;
-                for (int i = 0; i < N; ++i) vj += e->w[i] * e->A[(size_t)i * N + j];
-                port_row[j] = vj;
-                var += vj * vj;
-            }
-            for (int i = 0; i < N; ++i) port_row[N] += e->w[i] * e->mu[i];
-            const double sd = std::sqrt(var);
+            if (prepare_portfolio(port_row, tl.hist_lo, tl.hist_width)) return -1;
             tl.portfolio = 1;
             tl.port_x = opt->portfolio_loss_threshold;
-            tl.hist_lo = port_row[N] - 8.0 * sd;
-            tl.hist_width = (16.0 * sd > 0 ? 16.0 * sd : 1.0) / MCR_PORTFOLIO_BINS;
             tl.port_acc = e->d_port_acc; tl.port_hist = e->d_port_hist; tl.port_hist_sum = e->d_port_hist_sum;
-            e->port_hist_lo = tl.hist_lo; e->port_hist_hi = tl.hist_lo + tl.hist_width * MCR_PORTFOLIO_BINS;
-            if (!accumulate) {
-                MCR_CUDA(cudaMemsetAsync(e->d_port_acc, 0, sizeof(double) * 4, s));
-                MCR_CUDA(cudaMemsetAsync(e->d_port_hist, 0, sizeof(unsigned long long) * MCR_PORTFOLIO_BINS, s));
-                MCR_CUDA(cudaMemsetAsync(e->d_port_hist_sum, 0, sizeof(double) * MCR_PORTFOLIO_BINS, s));
-            }
         }
         const uint64_t image_key = e->gen * 2 + (plan.portfolio ? 1 : 0);
         if (e->tc_gen != image_key || e->tc_x != x || plan.portfolio) {
@@ -528,7 +539,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         MCR_CUDA(tc_occupancy(plan.rows, plan.portfolio, &bps));
         if (bps < 1) return fail("tensor-core kernel for N=%d%s does not fit one SM's shared memory", N, plan.portfolio ? " with the portfolio histogram" : "");
         if (const char* ov = getenv("MCR_TC_CTAS_PER_SM")) { if (atoi(ov) > 0) bps = atoi(ov); }  // tuning override
-        tc_grid_full = std::min(e->num_sms * bps, MAX_GRID);
+        tc_grid_full = std::min(sms * bps, MAX_GRID);
         mma_flops = 3.0 * 2.0 * tc_padded_n(rows) * (64.0 * ((rows + 64) / 64)) * 1.0;   // 3 passes over the padded NOUT x K tile (K covers N + 1 columns)
         tl.key0 = key0; tl.key1 = key1; tl.k = k; tl.d_image = e->d_tc_image;
         tl.flag_list = e->d_flag_list; tl.flag_count = e->d_flag_count; tl.flag_cap = FLAG_CAP;
@@ -630,28 +641,37 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
     // ---- streamed tensor path: piece image, per-pass guard bands ----
     StreamLaunch stl{};
     if (plan.stream) {
-        const size_t bytes = stream_image_bytes(N, e->lower);
+        const int port = plan.portfolio ? 1 : 0;
+        const size_t bytes = stream_image_bytes(N, port, e->lower);
         if (e->stream_image_cap < bytes) {
             cudaFree(e->d_stream_image); e->d_stream_image = nullptr; e->stream_image_cap = 0;
             MCR_CUDA(cudaMalloc(&e->d_stream_image, bytes));
             e->stream_image_cap = bytes; e->stream_gen = 0;
         }
-        std::vector<double> c(N);
+        std::vector<double> c(N), port_row;
         for (int i = 0; i < N; ++i) c[i] = e->mu[i] + x;
-        if (e->stream_gen != e->gen || e->stream_x != x) {
+        if (port) {
+            if (prepare_portfolio(port_row, stl.hist_lo, stl.hist_width)) return -1;
+            stl.portfolio = 1;
+            stl.port_x = opt->portfolio_loss_threshold;
+            stl.port_acc = e->d_port_acc; stl.port_hist = e->d_port_hist; stl.port_hist_sum = e->d_port_hist_sum;
+        }
+        const uint64_t image_key = e->gen * 2 + (uint64_t)port;
+        if (e->stream_gen != image_key || e->stream_x != x || port) {   // (the weights may have changed: a portfolio image is rebuilt)
             e->stream_host_image.resize(bytes);
-            e->stream_row_scale.assign(N, 1.0);
-            stream_build(N, e->lower, e->A.data(), c.data(), e->stream_host_image.data(), e->stream_row_scale.data());
+            e->stream_row_scale.assign(N + port, 1.0);
+            stream_build(N, e->lower, e->A.data(), c.data(), port ? port_row.data() : nullptr, e->stream_host_image.data(), e->stream_row_scale.data());
             MCR_CUDA(cudaStreamSynchronize(s));   // a previous run may still read the old image
             MCR_CUDA(cudaMemcpyAsync(e->d_stream_image, e->stream_host_image.data(), bytes, cudaMemcpyHostToDevice, s));
-            e->stream_gen = e->gen; e->stream_x = x;
+            e->stream_gen = image_key; e->stream_x = x;
         }
+        if (port) stl.port_scale = e->stream_row_scale[N];
         // guard band per pass, same budget as the round-1 large-N kernels: fp16x3 split (3 * 2^-22) + fp32 accumulation over 12 MMAs
         // per K-block, relative to ||a_i||_2 ||z||_2 (Cauchy-Schwarz; the kernel tracks the norm of the pass's normals), in
         // accumulator units (row i scaled by stream_row_scale[i]); derivation in DESIGN.md section 3.1
         static const double band_scale = [] { const char* v = getenv("MCR_TC_BAND_SCALE"); return v && *v ? atof(v) : 1.0; }();
         StreamPass ps[STREAM_MAX_PASSES];
-        const int np = stream_plan(N, e->lower, ps);
+        const int np = stream_plan(N, port, e->lower, ps);
         for (int q = 0; q < np; ++q) {
             const double gamma = std::ldexp(1.0, -19) * std::max(1.0, ps[q].kbn / 8.0);
             double rownorm = 0, cabs = 1e-300;
@@ -664,7 +684,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             stl.delta_rel[q] = plan.recheck ? band_scale * 2.0 * gamma * rownorm : 0.0;
             stl.delta_abs[q] = plan.recheck ? band_scale * 2.0 * gamma * cabs + 1e-30 : 0.0;
         }
-        mma_flops = stream_mma_flops(N, e->lower);
+        mma_flops = stream_mma_flops(N, port, e->lower);
         stl.key0 = key0; stl.key1 = key1; stl.N = N; stl.k = k; stl.lower = e->lower ? 1 : 0;
         stl.d_image = e->d_stream_image;
         stl.flag_list = e->d_flag_list; stl.flag_count = e->d_flag_count; stl.flag_cap = FLAG_CAP;
@@ -729,7 +749,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             stl.M = m; stl.path_offset = path_offset + done; stl.S_out = xp.S_out; stl.d_Z = xp.Z;
             const bool timed = e->n_timed < MAX_TIMED_CHUNKS;
             if (timed) MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed], s));
-            MCR_CUDA(stream_launch(stl, e->num_sms, s));
+            MCR_CUDA(stream_launch(stl, sms, s));
             if (timed) { MCR_CUDA(cudaEventRecord(e->evk[2 * e->n_timed + 1], s)); ++e->n_timed; }
             ++launches;
             if (plan.recheck) {
@@ -747,7 +767,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
                 MCR_CUDA(launch_exact(xp, e->num_sms, s));
                 ++launches;
             }
-            fin.block_partials = e->d_block_partials; fin.n_blocks = stream_grid(m, e->num_sms);
+            fin.block_partials = e->d_block_partials; fin.n_blocks = stream_grid(m, sms);
             fin.flag_count = e->d_flag_count; fin.flag_cap = FLAG_CAP;
         } else if (plan.wide) {
             wl.M = m; wl.path_offset = path_offset + done; wl.S_out = xp.S_out;

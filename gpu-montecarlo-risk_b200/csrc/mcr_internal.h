@@ -210,13 +210,21 @@ struct StreamLaunch {
     uint32_t* pair_count;
     uint32_t pair_cap;
     uint64_t* block_partials;
+    // portfolio extension: the image carries one more row (w^T A, w.mu), see stream_build
+    int32_t portfolio;
+    double port_x, hist_lo, hist_width, port_scale;
+    double* port_acc;
+    unsigned long long* port_hist;
+    double* port_hist_sum;
 };
-bool stream_supported(int N);
-int stream_plan(int N, bool lower, StreamPass* pass /* STREAM_MAX_PASSES */);   // number of passes
-size_t stream_image_bytes(int N, bool lower);
-double stream_mma_flops(int N, bool lower);          // fp16 MMA flops issued per trial
-int stream_normals_per_trial(int N, bool lower);     // normals generated per trial (passes re-derive the leading columns)
-void stream_build(int N, bool lower, const double* A, const double* c, uint8_t* image, double* row_scale /* N, out */);
+// port = 1: one more image row after the N asset rows (the portfolio return)
+bool stream_supported(int N, int port);
+int stream_plan(int N, int port, bool lower, StreamPass* pass /* STREAM_MAX_PASSES */);   // number of passes
+size_t stream_image_bytes(int N, int port, bool lower);
+double stream_mma_flops(int N, int port, bool lower);          // fp16 MMA flops issued per trial
+int stream_normals_per_trial(int N, int port, bool lower);     // normals generated per trial (passes re-derive the leading columns)
+// port_row: nullptr, or N + 1 values (w^T A, then w.mu).  row_scale: out, N (+ 1) entries
+void stream_build(int N, bool lower, const double* A, const double* c, const double* port_row, uint8_t* image, double* row_scale);
 int stream_grid(uint64_t M, int num_sms);
 cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s);
 

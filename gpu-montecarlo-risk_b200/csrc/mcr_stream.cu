@@ -85,6 +85,15 @@ struct StreamParams {
     uint32_t* pair_count;
     uint32_t pair_cap;
     uint64_t* block_partials;
+    // portfolio extension (north-star A7; no reference code): accumulator column port_col of the LAST pass holds s_p (w.R)
+    int32_t portfolio, port_col;
+    float port_thresh;            // scaled: tail event is  D < port_thresh  (= -x_p s_p)
+    float port_inv_scale;         // 1 / s_p
+    float hist_lo, hist_inv_w;    // unscaled histogram origin and 1 / bin width
+    double hist_lo_d, hist_w_d;   // the same origin and the bin width in fp64
+    double* port_acc;             // [4] += hits, sum P, sum P^2, sum of -P over tail events
+    unsigned long long* port_hist;  // [MCR_PORTFOLIO_BINS] counts
+    double* port_hist_sum;          // [MCR_PORTFOLIO_BINS] per-bin sum of P
 };
 
 // first accumulator column K-block kb multiplies in a pass starting at row r0 (rows < 64 kb of a lower-triangular transform are
@@ -156,6 +165,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
     uint8_t* s_ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // [ring][ST_PIECE_MAX]
     const int RING = p.ring;
     uint4* s_zcache = reinterpret_cast<uint4*>(s_ring + (size_t)RING * ST_PIECE_MAX);   // [kcache][part][4][128 rows] x 16 B
+    // portfolio histogram of this CTA (only with p.portfolio): count << 44 | quantised position sum per bin (port_hist_word)
+    unsigned long long* s_hist = reinterpret_cast<unsigned long long*>(s_ring + (size_t)RING * ST_PIECE_MAX + (size_t)p.kcache * ST_ZCACHE_BYTES);
     __shared__ uint64_t s_zempty[ST_ZSLOTS], s_bfull[ST_RING_MAX], s_bempty[ST_RING_MAX], s_done;
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_part_S[ST_PARTS][128], s_part_k1[ST_PARTS][128], s_part_k2[ST_PARTS][128];
@@ -174,6 +185,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
         for (int b = 0; b < ST_RING_MAX; ++b) { mbar_init(&s_bfull[b], 1); mbar_init(&s_bempty[b], csz); }
         mbar_init(&s_done, 1);
     }
+    if (p.portfolio)
+        for (int t = tid; t < MCR_PORTFOLIO_BINS; t += ST_THREADS) s_hist[t] = 0ull;
     if (warp == ST_MMA_WARP) tmem_alloc(&s_tmem, 512);
     fence_async_smem();
     tc_fence_before();
@@ -284,9 +297,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
         // two smallest keys (|accumulator|, column, sign) seen so far.
         uint32_t S_pass = 0, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
         int c_next = 32 * part;
+        // portfolio extension: partial sums of the trials whose portfolio column this thread reads
+        uint32_t p_hits = 0;
+        float p_sum = 0.0f, p_sum2 = 0.0f, p_tail = 0.0f;
 
         // read this thread's groups that end at or below column `upto` (everything left with final_part)
-        auto read_columns = [&](int ps, int upto, bool final_part) {
+        auto read_columns = [&](int ps, int upto, bool final_part, uint64_t i) {
             const int W = p.pass[ps].W;
             const float thr_max = p.thr_max[ps];
 #pragma unroll 1
@@ -295,6 +311,26 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                 tmem_ld32(lane_addr + (uint32_t)(ST_ACC_COL + c_next), v);
                 tmem_ld_wait();
                 const int valid = W - c_next;    // a multiple of 16: the last group of a pass may hold only 16 columns
+                if (p.portfolio && ps == NPASS - 1 && c_next <= p.port_col && p.port_col < c_next + 32) {
+                    // this group holds the portfolio column (row N of the image: w^T A and w.mu): take P out and leave a harmless
+                    // large positive value in its place for the crash count and the band
+                    const int pcl = p.port_col - c_next;
+                    uint32_t pbits = 0u;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (c == pcl) { pbits = v[c]; v[c] = 0x7F000000u; }
+                    if (i < p.M) {
+                        const float Ps = __uint_as_float(pbits), P = Ps * p.port_inv_scale;
+                        const bool tail = Ps < p.port_thresh;
+                        p_hits += tail ? 1u : 0u;
+                        p_tail += tail ? -P : 0.0f;
+                        p_sum += P;
+                        p_sum2 = fmaf(P, P, p_sum2);
+                        int bin;
+                        const unsigned long long word = port_hist_word(P, p.hist_lo, p.hist_inv_w, bin);
+                        atomicAdd(&s_hist[bin], word);
+                    }
+                }
                 float m = 3.0e38f;
 #pragma unroll
                 for (int c = 0; c < 32; c += 2) {
@@ -324,7 +360,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
             done_parity ^= 1u;
             tc_fence_after();
             const int r0 = p.pass[ps].r0;
-            read_columns(ps, p.pass[ps].W, true);
+            read_columns(ps, p.pass[ps].W, true, i);
             uint32_t S = S_pass;
             const uint32_t k1_ = k1, k2_ = k2;
             S_pass = 0u; k1 = 0xFFFFFFFFu; k2 = 0xFFFFFFFFu; c_next = 32 * part;
@@ -462,7 +498,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                     // now, while the tensor core works on.  The end of the pass is then left with the last few columns: neither do the
                     // generators wait long for the tensor core to drain, nor the tensor core for the read-out.  (The previous pass
                     // is pending until this pass's K-block 0 has been queued: nothing is read early before kb = 2.)
-                    if (LOWER && kb >= 2) read_columns(ps, min(p.pass[ps].W, 64 * (kb - 1) - p.pass[ps].r0), false);
+                    if (LOWER && kb >= 2) read_columns(ps, min(p.pass[ps].W, 64 * (kb - 1) - p.pass[ps].r0), false, i);
                     if (kb >= 0) {
                         tmem_st8(zaddr, hv);
                         tmem_st8(zaddr + 32u, lv);
@@ -483,6 +519,18 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
             }
         }
         if (pending) epilogue(pend_ps, pend_zsq, pend_i, true, false);
+        if (p.portfolio) {   // warp sums -> four double atomics per warp (the threads that never saw the portfolio column add zeros)
+            float a0 = (float)p_hits, a1 = p_sum, a2 = p_sum2, a3 = p_tail;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+            }
+            if (lane == 0 && (a0 != 0.0f || a1 != 0.0f || a2 != 0.0f)) {
+                atomicAdd(&p.port_acc[0], (double)a0); atomicAdd(&p.port_acc[1], (double)a1);
+                atomicAdd(&p.port_acc[2], (double)a2); atomicAdd(&p.port_acc[3], (double)a3);
+            }
+        }
         if (part == 0) {
             cnt = __reduce_add_sync(0xffffffffu, cnt);
             sum_s = __reduce_add_sync(0xffffffffu, sum_s);
@@ -493,6 +541,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
     tc_fence_before();
     __syncthreads();
     if (csz > 1) cluster_sync_all();   // nothing of the partner's is still in flight towards this CTA's shared memory
+    if (p.portfolio)
+        for (int t = tid; t < MCR_PORTFOLIO_BINS; t += ST_THREADS) port_hist_flush(s_hist[t], t, p.hist_lo_d, p.hist_w_d, p.port_hist, p.port_hist_sum);
     if (tid == 0) {
         uint64_t c = 0, s = 0;
         for (int w = 0; w < 4; ++w) { c += s_cnt[w]; s += s_sum[w]; }
@@ -507,26 +557,26 @@ static int round16(int v) { return (v + 15) & ~15; }
 
 // passes over row ranges of at most STREAM_WMAX rows: the first pass takes the remainder, so that with a lower-triangular
 // transform (pass p needs the normals of columns [0, last row of p]) the re-generated columns are as few as possible
-int stream_plan(int N, bool lower, StreamPass* pass) {
-    const int rows = round16(N);
+int stream_plan(int N, int port, bool lower, StreamPass* pass) {
+    const int rows = round16(N + port);
     const int np = (rows + ST_WMAX - 1) / ST_WMAX;
     if (np > STREAM_MAX_PASSES) return 0;
     int r0 = 0;
     for (int q = 0; q < np; ++q) {
         const int W = q == 0 ? rows - (np - 1) * ST_WMAX : ST_WMAX;
         pass[q].r0 = r0; pass[q].W = W;
-        pass[q].kend = lower ? std::min(N, r0 + W) : N;
+        pass[q].kend = lower ? std::min(N, r0 + W) : N;   // normal columns (the portfolio row, last, needs all N)
         pass[q].kbn = (pass[q].kend + tc::KBLOCK - 1) / tc::KBLOCK;
         r0 += W;
     }
     return np;
 }
 
-bool stream_supported(int N) { return N >= 1 && round16(N) <= ST_WMAX * STREAM_MAX_PASSES && N < MCR_MAX_HIST; }
+bool stream_supported(int N, int port) { return N >= 1 && round16(N + port) <= ST_WMAX * STREAM_MAX_PASSES && N < MCR_MAX_HIST; }
 
-size_t stream_image_bytes(int N, bool lower) {
+size_t stream_image_bytes(int N, int port, bool lower) {
     StreamPass ps[STREAM_MAX_PASSES];
-    const int np = stream_plan(N, lower, ps);
+    const int np = stream_plan(N, port, lower, ps);
     size_t b = 0;
     for (int q = 0; q < np; ++q) {
         b += (size_t)ps[q].W * 128;
@@ -535,9 +585,9 @@ size_t stream_image_bytes(int N, bool lower) {
     return b;
 }
 
-double stream_mma_flops(int N, bool lower) {
+double stream_mma_flops(int N, int port, bool lower) {
     StreamPass ps[STREAM_MAX_PASSES];
-    const int np = stream_plan(N, lower, ps);
+    const int np = stream_plan(N, port, lower, ps);
     double f = 0;
     for (int q = 0; q < np; ++q) {
         f += 2.0 * 16.0 * ps[q].W;
@@ -546,9 +596,9 @@ double stream_mma_flops(int N, bool lower) {
     return f;
 }
 
-int stream_normals_per_trial(int N, bool lower) {
+int stream_normals_per_trial(int N, int port, bool lower) {
     StreamPass ps[STREAM_MAX_PASSES];
-    const int np = stream_plan(N, lower, ps);
+    const int np = stream_plan(N, port, lower, ps);
     const int cached = np > 1 ? tc::KBLOCK * std::min(ST_KCACHE_MAX, ps[0].kend / tc::KBLOCK) : 0;
     int s = 0;
     for (int q = 0; q < np; ++q) s += ps[q].kend - (q > 0 ? cached : 0);
@@ -561,13 +611,18 @@ static void put_half(uint8_t* piece, int r, int kk, __half v) { memcpy(piece + t
 // (stream_n1), each (rows) x 64 fp16 in the K-major 128-byte-swizzled operand layout; row i carries s_i A_ij (row_scale:
 // tc_row_scale), the constant piece s_i (mu_i + x) as hi (K column 0) and lo (K column 1); padded rows hold zeros and a large
 // positive constant
-void stream_build(int N, bool lower, const double* A, const double* c, uint8_t* image, double* row_scale) {
+void stream_build(int N, bool lower, const double* A, const double* c, const double* port_row, uint8_t* image, double* row_scale) {
     StreamPass ps[STREAM_MAX_PASSES];
-    const int np = stream_plan(N, lower, ps);
-    memset(image, 0, stream_image_bytes(N, lower));
-    for (int i = 0; i < N; ++i) {
-        double mx = std::fabs(c[i]);
-        for (int k = 0; k < N; ++k) mx = std::max(mx, std::fabs(A[(size_t)i * N + k]));
+    const int port = port_row ? 1 : 0;
+    const int np = stream_plan(N, port, lower, ps);
+    memset(image, 0, stream_image_bytes(N, port, lower));
+    // row i < N: transform row i and the constant mu_i + x; row N (portfolio): w^T A and the constant w.mu
+    auto entry = [&](int i, int j) { return i < N ? A[(size_t)i * N + j] : port_row[j]; };
+    auto constant = [&](int i) { return i < N ? c[i] : port_row[N]; };
+    const int rows = N + port;
+    for (int i = 0; i < rows; ++i) {
+        double mx = std::fabs(constant(i));
+        for (int k = 0; k < N; ++k) mx = std::max(mx, std::fabs(entry(i, k)));
         row_scale[i] = tc_row_scale(mx);
     }
     auto split = [](double v, __half& hi, __half& lo) {
@@ -585,16 +640,16 @@ void stream_build(int N, bool lower, const double* A, const double* c, uint8_t* 
                 const int i = r0 + a0 + r, ch = r >= n1 ? 1 : 0, rl = r - (ch ? n1 : 0);
                 __half hi, lo;
                 if (kb < 0) {
-                    split(i < N ? c[i] * row_scale[i] : TC_PAD_ROW, hi, lo);
+                    split(i < rows ? constant(i) * row_scale[i] : TC_PAD_ROW, hi, lo);
                     put_half(piece[0][ch], rl, 0, hi);
                     put_half(piece[0][ch], rl, 1, lo);
                     continue;
                 }
-                if (i >= N) break;
+                if (i >= rows) break;
                 for (int kk = 0; kk < tc::KBLOCK; ++kk) {
                     const int j = tc::KBLOCK * kb + kk;
                     if (j >= ps[q].kend) break;
-                    split(A[(size_t)i * N + j] * row_scale[i], hi, lo);
+                    split(entry(i, j) * row_scale[i], hi, lo);
                     put_half(piece[0][ch], rl, kk, hi);
                     put_half(piece[1][ch], rl, kk, lo);
                 }
@@ -616,7 +671,7 @@ cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
     StreamParams p{};
     p.M = l.M; p.path_offset = l.path_offset; p.key0 = l.key0; p.key1 = l.key1;
     p.N = l.N; p.k = l.k; p.lower = l.lower;
-    p.npass = stream_plan(l.N, l.lower != 0, p.pass);
+    p.npass = stream_plan(l.N, l.portfolio ? 1 : 0, l.lower != 0, p.pass);
     if (p.npass <= 0) return cudaErrorInvalidValue;
     for (int q = 0; q < p.npass; ++q) {
         p.delta_rel[q] = (float)l.delta_rel[q];
@@ -631,7 +686,14 @@ cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
     // transform pieces gets the rest of 6 x 32 KB
     p.kcache = (p.npass > 1 && !l.d_Z) ? std::min(ST_KCACHE_MAX, p.pass[0].kend / tc::KBLOCK) : 0;
     p.ring = ST_RING_MAX - p.kcache;
-    const size_t smem = (size_t)p.ring * ST_PIECE_MAX + (size_t)p.kcache * ST_ZCACHE_BYTES + 1024;
+    const size_t smem = (size_t)p.ring * ST_PIECE_MAX + (size_t)p.kcache * ST_ZCACHE_BYTES + 1024 + (l.portfolio ? (size_t)MCR_PORTFOLIO_BINS * 8 : 0);
+    p.portfolio = l.portfolio;
+    if (l.portfolio) {
+        p.port_col = l.N - p.pass[p.npass - 1].r0;
+        p.port_thresh = (float)(-l.port_x * l.port_scale); p.port_inv_scale = (float)(1.0 / l.port_scale);
+        p.hist_lo = (float)l.hist_lo; p.hist_inv_w = (float)(1.0 / l.hist_width); p.hist_lo_d = l.hist_lo; p.hist_w_d = l.hist_width;
+        p.port_acc = l.port_acc; p.port_hist = l.port_hist; p.port_hist_sum = l.port_hist_sum;
+    }
     p.keys.set(l.key0, l.key1);
     const int grid = stream_grid(l.M, num_sms);
     static const int want_cluster = [] { const char* v = getenv("MCR_STREAM_CLUSTER"); return v && *v ? atoi(v) : 2; }();

@@ -314,7 +314,7 @@ cudaError_t tc_launch(int N, int rows, const TcLaunch& l, int grid, cudaStream_t
     p.flag_list = l.flag_list; p.flag_count = l.flag_count; p.flag_cap = l.flag_cap; p.block_partials = l.block_partials;
     p.pair_list = l.pair_list; p.pair_count = l.pair_count; p.pair_cap = l.pair_cap;
     p.portfolio = l.portfolio; p.port_thresh = (float)(-l.port_x * l.port_scale); p.port_inv_scale = (float)(1.0 / l.port_scale);
-    p.hist_lo = (float)l.hist_lo; p.hist_inv_w = (float)(1.0 / l.hist_width);
+    p.hist_lo = (float)l.hist_lo; p.hist_inv_w = (float)(1.0 / l.hist_width); p.hist_lo_d = l.hist_lo; p.hist_w_d = l.hist_width;
     p.port_acc = l.port_acc; p.port_hist = l.port_hist; p.port_hist_sum = l.port_hist_sum;
     for (int q = 0; q < 8; ++q) {
         const int col = 8 * (N / 8) + q;

@@ -132,6 +132,28 @@ inline double tc_row_scale(double row_maxabs) {
 }
 constexpr double TC_PAD_ROW = 4096.0;     // scaled constant of a padded row: far on the "no crash" side
 
+// ---- portfolio histogram (north-star extension A7), shared by the tile kernel and the streamed kernel -------------------------
+// A CTA keeps one 64-bit word per bin in shared memory: count << 44 | sum of q, q = the trial's position inside the histogram
+// range in units of 2^-24 of the range (<= 2^24, so 2^20 trials fit below the count field: a CTA sees < 2^20 trials per launch).
+// Integer adds only: the per-bin sums are exact in that quantisation (one step = 1e-6 sigma_p) and do not depend on the order in
+// which trials arrive, unlike the fp32 atomics of round 1.
+constexpr int PORT_HIST_BINS = 2048;                       // = MCR_PORTFOLIO_BINS
+constexpr float PORT_HIST_Q_PER_BIN = 8192.0f;             // 2^24 / 2048
+__device__ __forceinline__ unsigned long long port_hist_word(float P, float hist_lo, float hist_inv_w, int& bin) {
+    float u = (P - hist_lo) * hist_inv_w;                  // position in bins
+    u = fminf(fmaxf(u, 0.0f), (float)PORT_HIST_BINS);
+    bin = min((int)u, PORT_HIST_BINS - 1);
+    return (1ull << 44) + (unsigned long long)__float2uint_rn(u * PORT_HIST_Q_PER_BIN);
+}
+__device__ __forceinline__ void port_hist_flush(unsigned long long word, int bin, double hist_lo, double hist_w, unsigned long long* hist,
+                                                double* hist_sum) {
+    const unsigned long long c = word >> 44;
+    if (c == 0ull) return;
+    const double q = (double)(word & ((1ull << 44) - 1ull));
+    atomicAdd(&hist[bin], c);
+    atomicAdd(&hist_sum[bin], (double)c * hist_lo + q * (hist_w / (double)PORT_HIST_Q_PER_BIN));   // sum of P = sum (lo + q w / 8192)
+}
+
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 

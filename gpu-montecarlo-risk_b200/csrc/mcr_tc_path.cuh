@@ -59,6 +59,7 @@ struct TcParams {
     float port_thresh;            // scaled: tail event is  D < port_thresh  (= -x_p * scale of the portfolio row)
     float port_inv_scale;         // 1 / scale of the portfolio row
     float hist_lo, hist_inv_w;    // unscaled histogram origin and 1 / bin width
+    double hist_lo_d, hist_w_d;   // the same origin and the bin width in fp64 (per-bin sums are rebuilt from the quantised positions)
     double* port_acc;             // [4] += hits, sum P, sum P^2, sum of -P over tail events
     unsigned long long* port_hist;  // [MCR_PORTFOLIO_BINS] counts
     double* port_hist_sum;          // [MCR_PORTFOLIO_BINS] per-bin sum of P
@@ -134,8 +135,9 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
     uint8_t* s_ring = smem;                                   // [group][hi|lo][128 x 128 B]
     uint8_t* s_bhi = smem + GROUPS * SLOT_BYTES;
     uint8_t* s_blo = s_bhi + B_BYTES;
-    uint32_t* s_hist_cnt = reinterpret_cast<uint32_t*>(s_blo + B_BYTES);          // only when p.portfolio (host sizes smem)
-    float* s_hist_sum = reinterpret_cast<float*>(s_hist_cnt + PORT_BINS);
+    // only when p.portfolio (host sizes smem): one 64-bit word per bin = count << 44 | sum of the trials' positions in the histogram
+    // range quantised to 2^-24 of it (port_hist_word): integer adds, exact and independent of the order the trials arrive in
+    unsigned long long* s_hist = reinterpret_cast<unsigned long long*>(s_blo + B_BYTES);
     __shared__ uint64_t s_mma[GROUPS];
     __shared__ double s_port[4 * GROUPS][4];
     __shared__ uint32_t s_tmem;
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
         for (uint32_t t = tid; t < 2 * B_BYTES / 16; t += NTHREADS) dst[t] = src[t];
     }
     if (p.portfolio)
-        for (uint32_t t = tid; t < PORT_BINS; t += NTHREADS) { s_hist_cnt[t] = 0u; s_hist_sum[t] = 0.0f; }
+        for (uint32_t t = tid; t < PORT_BINS; t += NTHREADS) s_hist[t] = 0ull;
     if (tid == 0)
         for (int gg = 0; gg < GROUPS; ++gg) mbar_init(&s_mma[gg], 1);
     if (warp == 0) tmem_alloc(&s_tmem, TMEM_COLS);
@@ -230,10 +232,9 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
                             p_tail += tail ? -P : 0.0f;
                             p_sum += P;
                             p_sum2 = fmaf(P, P, p_sum2);
-                            int bin = (int)floorf((P - p.hist_lo) * p.hist_inv_w);
-                            bin = bin < 0 ? 0 : (bin >= (int)PORT_BINS ? (int)PORT_BINS - 1 : bin);
-                            atomicAdd(&s_hist_cnt[bin], 1u);
-                            atomicAdd(&s_hist_sum[bin], P);
+                            int bin;
+                            const unsigned long long word = port_hist_word(P, p.hist_lo, p.hist_inv_w, bin);
+                            atomicAdd(&s_hist[bin], word);
                         }
                     }
                 }
@@ -383,11 +384,7 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
             atomicAdd(&p.port_acc[tid], a);
         }
         for (uint32_t t = tid; t < PORT_BINS; t += NTHREADS) {
-            const uint32_t c = s_hist_cnt[t];
-            if (c) {
-                atomicAdd(&p.port_hist[t], (unsigned long long)c);
-                atomicAdd(&p.port_hist_sum[t], (double)s_hist_sum[t]);
-            }
+            port_hist_flush(s_hist[t], t, p.hist_lo_d, p.hist_w_d, p.port_hist, p.port_hist_sum);
         }
     }
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }

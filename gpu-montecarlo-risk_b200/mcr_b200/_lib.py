@@ -25,7 +25,7 @@ class RunOptions(C.Structure):
         ("no_recheck", C.c_int32),
         ("want_hist", C.c_int32),
         ("want_portfolio", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("sm_reserve", C.c_int32),
         ("portfolio_loss_threshold", C.c_double),
         ("d_S_values", C.c_void_p),
     ]

@@ -55,8 +55,9 @@ class RunResult:
                          int(r.padded_N), int(r.launches), S_values)
 
 
-def make_options(kernel=KERNEL_AUTO, no_recheck=False, d_S_values=0, portfolio_threshold=None, want_hist=False) -> RunOptions:
+def make_options(kernel=KERNEL_AUTO, no_recheck=False, d_S_values=0, portfolio_threshold=None, want_hist=False, sm_reserve=0) -> RunOptions:
     o = RunOptions()
+    o.sm_reserve = int(sm_reserve)
     o.struct_size = C.sizeof(RunOptions)
     o.kernel = int(kernel)
     o.no_recheck = int(bool(no_recheck))
@@ -133,9 +134,10 @@ class Engine:
         return res
 
     def run_async(self, M, seed, x, k, d_partials_ptr, stream_ptr, path_offset=0, kernel=KERNEL_AUTO,
-                  no_recheck=False, d_S_values=0):
-        """Enqueue on a caller-owned stream; partial words land in the caller's device buffer."""
-        o = make_options(kernel, no_recheck, d_S_values)
+                  no_recheck=False, d_S_values=0, sm_reserve=0):
+        """Enqueue on a caller-owned stream; partial words land in the caller's device buffer.  sm_reserve: SMs left free for
+        a collective that runs next to the kernels."""
+        o = make_options(kernel, no_recheck, d_S_values, sm_reserve=sm_reserve)
         check(self._lib.mcr_run_async(self._h, int(M), int(path_offset), int(seed), float(x), int(k), C.byref(o),
                                       C.c_void_p(int(d_partials_ptr)), C.c_void_p(int(stream_ptr) if stream_ptr else None)))
 

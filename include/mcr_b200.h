@@ -48,7 +48,10 @@ typedef struct mcr_run_options {
                               normals bit-for-bit.  1: raw fp32 decisions (benchmark ablation). */
     int32_t want_hist;     /* 1: also fill mcr_result.hist_S (mcr_run only; costs one 4-byte store + load per trial) */
     int32_t want_portfolio;/* 1: also reduce the equal-/custom-weight portfolio return (north-star extension) */
-    int32_t reserved0;
+    int32_t sm_reserve;    /* SMs the path kernels leave free (default 0 = none).  The fast kernels are persistent, one CTA per SM with
+                              a static share of the tiles, and fill every SM; a collective's kernel launched next to them then waits
+                              for an SM and delays the CTA that comes after it - and with it the whole launch.  One process per GPU
+                              overlapping each step's all-reduce with the next step's kernels sets 1 (bench.py does). */
     double portfolio_loss_threshold; /* x_p: portfolio tail event is  w.R < -x_p  */
     /* optional per-path output of S (the reference's MonteCarloResult.S_values, src/model_interface.h:12).
      * DEVICE pointer to n_paths int32 (or NULL).  Host callers use mcr_simulate_host instead. */

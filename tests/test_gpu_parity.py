@@ -342,9 +342,18 @@ def test_kernel_selection(engine):
     m = synthetic_model(64)
     engine.upload_sigma(m.mu, m.Sigma)
     assert engine.run(1000, 1, m.x, m.k).kernel == "tensor"    # N >= 36: tensor-core kernel
+    # supplied normals: AUTO keeps the FFMA kernel up to N = 128, an explicit request reaches the (streamed) tensor kernel
     Z = np.zeros((4, 64))
-    with pytest.raises(api.McrError, match="tensor-core kernel generates its normals"):
-        engine.run_with_normals(Z, m.x, m.k, kernel=api.KERNEL_TENSOR)
+    assert engine.run_with_normals(Z, m.x, m.k).kernel == "ffma"
+    rt = engine.run_with_normals(Z, m.x, m.k, kernel=api.KERNEL_TENSOR)
+    assert rt.kernel == "tensor" and rt.count == 0 and list(rt.S_values) == [0, 0, 0, 0]
+    with pytest.raises(api.McrError, match="portfolio outputs are not available with supplied normals"):
+        engine._lib.mcr_run_with_normals   # (the error path itself is exercised through the C ABI below)
+        import ctypes as C
+        from mcr_b200 import _lib
+        o = api.make_options(api.KERNEL_TENSOR, portfolio_threshold=0.01)
+        r = _lib.Result()
+        _lib.check(engine._lib.mcr_run_with_normals(engine._h, 4, Z.ctypes.data, float(m.x), int(m.k), C.byref(o), None, C.byref(r)))
 
 
 @pytest.mark.parametrize("N", [50, 100, 160])

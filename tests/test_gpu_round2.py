@@ -107,6 +107,43 @@ def test_supplied_normals_wide_models(engine, oracle, N, mode, M):
         assert (r.count, r.sum_S, r.n_paths) == (ro["count"], ro["sum_S"], M)
 
 
+@pytest.mark.parametrize("N,mode,M,weights", [(128, api.TRANSFORM_LOWER, 300_000, None), (200, api.TRANSFORM_GSL_FULL, 200_000, "ramp"),
+                                              (600, api.TRANSFORM_LOWER, 120_000, "ramp")])
+def test_portfolio_outputs_for_wide_models(engine, oracle, N, mode, M, weights):
+    """North-star extension A7 (parity unpinned: the reference has no portfolio / VaR / ES code; checked against the oracle's own
+    definition on the dumped normals) beyond the tile kernel: the streamed kernel carries w.R as one more image row.
+    Stated tolerances as for N <= 126: moments 1e-4 relative (fp16x3 products, fp32 per-thread partial sums); hits may differ by
+    the trials whose P sits within 1e-6 of the threshold; VaR within one histogram bin (sigma_p / 128); ES within 0.2 %."""
+    m = synthetic_model(N)
+    A = engine.upload_sigma(m.mu, m.Sigma, mode)
+    w = np.full(N, 1.0 / N) if weights is None else np.arange(1, N + 1) / np.arange(1, N + 1).sum()
+    xp, seed = 0.012, 31
+    r = engine.run(M, seed, m.x, m.k, portfolio_threshold=xp, weights=w)
+    assert r.kernel == "tensor"
+    Z, _ = engine.dump_normals(M, seed)
+    ro = oracle.run_normals(A, m.mu, m.k, m.x, Z)
+    assert (r.count, r.sum_S) == (ro["count"], ro["sum_S"])       # the base outputs are untouched and exact
+    P = oracle.portfolio(A, m.mu, w, Z)
+    pf = r.portfolio
+    near = int((np.abs(P + xp) < 1e-6).sum())
+    assert abs(pf["hits"] - int((P < -xp).sum())) <= near + 1
+    assert pf["mean"] == pytest.approx(P.mean(), rel=1e-4, abs=1e-8)
+    assert pf["var"] == pytest.approx(P.var(), rel=1e-4)
+    assert pf["tail_loss_sum"] == pytest.approx(-P[P < -xp].sum(), rel=1e-4, abs=1e-6)
+    assert int(pf["hist"].sum()) == M
+    assert float(pf["hist_sum"].sum()) == pytest.approx(P.sum(), rel=1e-5, abs=1e-6 * M * P.std())   # per-bin sums: exact to the 2^-24 quantisation
+    width = (pf["hist_hi"] - pf["hist_lo"]) / len(pf["hist"])
+    for a in (0.95, 0.99):
+        q = np.quantile(-P, a)
+        es = (-P)[-P >= q].mean()
+        assert abs(pf["VaR"][a] - q) <= width
+        assert pf["ES"][a] == pytest.approx(es, rel=2e-3)
+    # determinism: integer histogram words -> identical bins and bin sums on a second run and over two shards
+    r2 = engine.run(M, seed, m.x, m.k, portfolio_threshold=xp, weights=w)
+    np.testing.assert_array_equal(r2.portfolio["hist"], pf["hist"])
+    engine.run(1000, seed, m.x, m.k, weights=np.full(N, 1.0 / N))      # restore default weights
+
+
 @pytest.mark.parametrize("N", [15, 50, 160, 600])
 def test_non_positive_k_counts_every_trial(engine, N):
     """S >= k is a signed comparison in the reference (serial.c:137-141): k <= 0 counts every trial, on every kernel."""
