@@ -269,11 +269,13 @@ def measured_peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1590.0, "hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the path kernel, from committed `ncu --set full` captures;
-# (kernel, N, trials per launch) -> (bytes, file).  Anything not captured reports null.
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the path kernel, from committed `ncu --set full` captures:
+# (kernel, N) -> (bytes, file).  The path kernels read the operand image / constant bank and the code once per launch and write
+# two words per CTA, whatever the number of trials (the captures ran 2e7 / 4e6 trials per launch); anything not captured is null.
 TRAFFIC_TABLE = {
-    ("tensor", 50, 100_000_000): (61440, "profiles/r01_bench_tc_n50_ncu_summary.txt"),
-    ("ffma", 50, 100_000_000): (71168, "profiles/r01_ffma_n50_pipelined_ncu_summary.txt"),
+    ("tensor", 50): (60416, "profiles/r02_tc_path_n50_ncu_summary.txt"),
+    ("ffma", 50): (71168, "profiles/r01_ffma_n50_pipelined_ncu_summary.txt"),
+    ("tensor", 600): (956416, "profiles/r02_stream_final_n600_ncu_summary.txt"),
 }
 
 
@@ -356,8 +358,9 @@ def tensor_roofline(N, kernel, padded_N, sims_per_launch, k_ms, step_ms, sims_pe
     CUDA-event time, against the measured bf16 peak (burst for the kernel alone, sustained for the whole step)."""
     alg = sims_per_launch * flops_per_sim(N) / (k_ms * 1e-3) / 1e12
     alg_step = sims_per_step * flops_per_sim(N) / (step_ms * 1e-3) / 1e12
+    tr = TRAFFIC_TABLE.get(("tensor", N))
     r = {"bound": "tensor", "achieved": alg, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": alg / peaks["bf16_burst"],
-         "traffic": None, "kernel": kernel, "kernel_ms_per_launch": k_ms, "flops_per_sim": flops_per_sim(N),
+         "traffic": tr[0] if tr else None, "traffic_source": tr[1] if tr else None, "kernel": kernel, "kernel_ms_per_launch": k_ms, "flops_per_sim": flops_per_sim(N),
          "frac_of_sustained_peak_over_step": alg_step / peaks["bf16_sustained"], "peak_source": peaks["source"],
          "note": "algorithmic flops F(N)=N^2+3N per simulation; the correlate runs as fp16x3 (hi*hi + lo*hi + hi*lo, fp32 accumulate "
                  "in TMEM), so the tensor pipe executes >= 3x the algorithmic work plus tile padding"}
@@ -472,7 +475,7 @@ def main():
                      "result": {"count": r.count, "sum_S": r.sum_S, "P_hat": r.P_hat, "n_rechecked": r.n_rechecked}}
             sims_per_launch = m_rank / max(1, kl)
             if n_assets > 128:
-                entry["roofline"] = tensor_roofline(n_assets, "tcgen05 fp16x3 correlate, N > 128 (DESIGN.md section 3.4)", one.padded_N,
+                entry["roofline"] = tensor_roofline(n_assets, "tc_stream_kernel (tcgen05 fp16x3 correlate, normals in TMEM, DESIGN.md section 3.4)", one.padded_N,
                                                     sims_per_launch, km, ms, m_rank, eng.mma_flops_per_trial(), peaks)
             else:
                 tf = sims_per_launch * flops_per_sim(n_assets) / (km * 1e-3) / 1e12
@@ -528,9 +531,9 @@ def main():
         # N > 128 kernels - is several launches): trials per launch = the step's trials / launches
         sims_per_launch = M / max(1, launches_per_kernel_step)
         achieved_tf = sims_per_launch * flops_per_sim(N) / (k_ms * 1e-3) / 1e12
-        traffic = TRAFFIC_TABLE.get((one.kernel, N, int(sims_per_launch)))
+        traffic = TRAFFIC_TABLE.get((one.kernel, N))
         if one.kernel == "tensor" and N > 128:
-            roof = tensor_roofline(N, "tcgen05 fp16x3 correlate, N > 128 (DESIGN.md section 3.4)", one.padded_N, sims_per_launch, k_ms,
+            roof = tensor_roofline(N, "tc_stream_kernel (tcgen05 fp16x3 correlate, normals in TMEM, DESIGN.md section 3.4)", one.padded_N, sims_per_launch, k_ms,
                                    ms_step, M, eng.mma_flops_per_trial(), peaks)
         else:
             tensor = None
