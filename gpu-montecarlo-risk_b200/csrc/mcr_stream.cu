@@ -53,7 +53,10 @@ constexpr int ST_ACC_COL = ST_ZSLOTS * ST_ZCOLS;     // first accumulator column
 constexpr int ST_CHUNK_MAX = 256;                    // rows of one transform piece = the N of the MMAs that read it
 constexpr uint32_t ST_PIECE_MAX = ST_CHUNK_MAX * 128;   // 32 KB: up to 256 rows x 64 fp16
 constexpr int ST_RING_MAX = 6;                       // transform pieces in flight (6 x 32 KB; 3 when the Z cache takes its share)
-constexpr int ST_KCACHE_MAX = 3;                     // K-blocks of normals kept in shared memory for the later passes (32 KB each)
+#ifndef MCR_STREAM_KCACHE_MAX
+#define MCR_STREAM_KCACHE_MAX 3
+#endif
+constexpr int ST_KCACHE_MAX = MCR_STREAM_KCACHE_MAX;                     // K-blocks of normals kept in shared memory for the later passes (32 KB each)
 constexpr uint32_t ST_ZCACHE_BYTES = 128 * 64 * 4;   // one K-block of Z: 128 trials x 64 columns x (hi + lo)
 constexpr int ST_PARTS = 4;                          // generator threads per trial: 16 of a K-block's 64 columns each
 constexpr int ST_GEN_THREADS = 128 * ST_PARTS;
@@ -158,7 +161,8 @@ __device__ __forceinline__ void split16(const float (&z)[16], uint32_t (&hv)[8],
     }
 }
 
-template <bool SUPPLIED>
+// PORT: the image carries the portfolio row (a separate instantiation: the plain kernel pays nothing for the extension)
+template <bool SUPPLIED, bool PORT>
 __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
         for (int b = 0; b < ST_RING_MAX; ++b) { mbar_init(&s_bfull[b], 1); mbar_init(&s_bempty[b], csz); }
         mbar_init(&s_done, 1);
     }
-    if (p.portfolio)
+    if (PORT)
         for (int t = tid; t < MCR_PORTFOLIO_BINS; t += ST_THREADS) s_hist[t] = 0ull;
     if (warp == ST_MMA_WARP) tmem_alloc(&s_tmem, 512);
     fence_async_smem();
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                 tmem_ld32(lane_addr + (uint32_t)(ST_ACC_COL + c_next), v);
                 tmem_ld_wait();
                 const int valid = W - c_next;    // a multiple of 16: the last group of a pass may hold only 16 columns
-                if (p.portfolio && ps == NPASS - 1 && c_next <= p.port_col && p.port_col < c_next + 32) {
+                if (PORT && ps == NPASS - 1 && c_next <= p.port_col && p.port_col < c_next + 32) {
                     // this group holds the portfolio column (row N of the image: w^T A and w.mu): take P out and leave a harmless
                     // large positive value in its place for the crash count and the band
                     const int pcl = p.port_col - c_next;
@@ -519,7 +523,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
             }
         }
         if (pending) epilogue(pend_ps, pend_zsq, pend_i, true, false);
-        if (p.portfolio) {   // warp sums -> four double atomics per warp (the threads that never saw the portfolio column add zeros)
+        if (PORT) {   // warp sums -> four double atomics per warp (the threads that never saw the portfolio column add zeros)
             float a0 = (float)p_hits, a1 = p_sum, a2 = p_sum2, a3 = p_tail;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -541,7 +545,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
     tc_fence_before();
     __syncthreads();
     if (csz > 1) cluster_sync_all();   // nothing of the partner's is still in flight towards this CTA's shared memory
-    if (p.portfolio)
+    if (PORT)
         for (int t = tid; t < MCR_PORTFOLIO_BINS; t += ST_THREADS) port_hist_flush(s_hist[t], t, p.hist_lo_d, p.hist_w_d, p.port_hist, p.port_hist_sum);
     if (tid == 0) {
         uint64_t c = 0, s = 0;
@@ -705,13 +709,17 @@ cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e;
     if (l.d_Z) {
-        e = cudaFuncSetAttribute(tc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(tc_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<true>, p);
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<true, false>, p);
+    } else if (l.portfolio) {
+        e = cudaFuncSetAttribute(tc_stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, true>, p);
     } else {
-        e = cudaFuncSetAttribute(tc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(tc_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false>, p);
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, false>, p);
     }
     return e != cudaSuccess ? e : cudaGetLastError();
 }
