@@ -91,6 +91,8 @@ PROTOTYPES = {
     "mcr_destroy": (C.c_int, [C.c_void_p]),
     "mcr_upload_model": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "mcr_set_portfolio_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "mcr_device_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mcr_device_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mcr_run": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_int,
                           C.POINTER(RunOptions), C.POINTER(Result)]),
     "mcr_run_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_int,

@@ -187,6 +187,23 @@ class Engine:
         check(self._lib.mcr_last_main_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def device_moments(self, returns):
+        """(mu, Sigma) = mean vector and sample covariance (ddof=1) of a T x N matrix of returns, computed on the device
+        (the reference's preprocessing_stats.compute_stats)."""
+        X = _f64(returns)
+        T, N = X.shape
+        mu, Sigma = np.zeros(N), np.zeros((N, N))
+        check(self._lib.mcr_device_moments(self._h, X.ctypes.data, T, N, mu.ctypes.data, Sigma.ctypes.data))
+        return mu, Sigma
+
+    def device_transform(self, Sigma, mode=TRANSFORM_LOWER) -> np.ndarray:
+        """build_transform on the device (same summation order: bitwise the host result)."""
+        Sigma = _f64(Sigma)
+        N = Sigma.shape[0]
+        A = np.zeros((N, N))
+        check(self._lib.mcr_device_transform(self._h, Sigma.ctypes.data, N, N, int(mode), A.ctypes.data))
+        return A
+
     def mma_flops_per_trial(self) -> float:
         """fp16 MMA flops per trial executed by the tensor pipe in the last run (0 for the FFMA / fp64 kernels)."""
         f = C.c_double(0)

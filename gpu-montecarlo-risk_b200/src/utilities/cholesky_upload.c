@@ -30,8 +30,21 @@ int mcr_prepare_model(const gsl_vector *mu, const gsl_matrix *Sigma, int mode, d
         return -1;
     }
     for (size_t i = 0; i < N; i++) m[i] = mu->data[i * mu->stride];
-    /* Sigma->tda is the row pitch; mcr_build_transform reads rows with that leading dimension */
-    if (mcr_build_transform(Sigma->data, (int)N, (int)Sigma->tda, mode, A) != 0) {
+    /* Sigma->tda is the row pitch; mcr_build_transform reads rows with that leading dimension.
+     * MCR_DEVICE_CHOLESKY=1: the same factorisation on the GPU (mcr_device_transform: same summation order, bitwise the same
+     * factor; worth it from a few hundred assets up). */
+    int rc;
+    const char *dev = getenv("MCR_DEVICE_CHOLESKY");
+    if (dev && *dev && strcmp(dev, "0") != 0) {
+        mcr_engine *e = NULL;
+        const char *fd = getenv("MCR_FIRST_DEVICE");
+        rc = mcr_create(fd && *fd ? atoi(fd) : 0, &e);
+        if (rc == 0) rc = mcr_device_transform(e, Sigma->data, (int)N, (int)Sigma->tda, mode, A);
+        mcr_destroy(e);
+    } else {
+        rc = mcr_build_transform(Sigma->data, (int)N, (int)Sigma->tda, mode, A);
+    }
+    if (rc != 0) {
         fprintf(stderr, "Error: Cholesky decomposition failed (%s)\n", mcr_last_error());
         free(m); free(A);
         return -1;

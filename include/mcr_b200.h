@@ -111,6 +111,14 @@ int mcr_upload_model(mcr_engine *e, int N, const double *mu, const double *A, in
 /* Optional portfolio weights for the extension outputs (default 1/N each). */
 int mcr_set_portfolio_weights(mcr_engine *e, const double *w, int N);
 
+/* ---- statistics and factorisation on the device -------------
+ * mcr_device_moments: mean vector and sample covariance (ddof = 1) of `returns` (HOST, T x N row-major fp64): what the
+ * reference's offline pipeline computes with pandas (preprocessing/preprocessing_stats.py:18,21) before save_binary.py writes
+ * mu.bin / sigma.bin.  mu_out: N, Sigma_out: N x N row-major (HOST).
+ * mcr_device_transform: mcr_build_transform on the device - same arguments, same summation order, BITWISE the same A.  */
+int mcr_device_moments(mcr_engine *e, const double *returns, int T, int N, double *mu_out, double *Sigma_out);
+int mcr_device_transform(mcr_engine *e, const double *Sigma, int N, int lds, int mode, double *A_out);
+
 /* ---- the hot path ----------------------------------------------------------------------- */
 /* Simulate trials [path_offset, path_offset + M) of the stream keyed by seed.  Normals come from
  * Philox4x32-10 with key = seed and counter = (path index, asset block), so any partition of the

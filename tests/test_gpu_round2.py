@@ -259,3 +259,56 @@ def test_reference_cuda_model_agrees_within_3_sigma(engine):
         se = np.sqrt(pr * (1 - pr) / M + po * (1 - po) / ours.n_paths)
         assert abs(pr - po) <= 3 * se, (N, pr, po, se)
         assert abs(r["S_values"].mean() - ours.sum_S / ours.n_paths) < 0.02 * max(r["S_values"].mean(), 1e-3) + 3e-3
+
+
+# ---------------------------------------------------------------- F4: statistics and factorisation on the device
+@pytest.mark.parametrize("N", [15, 50, 200, 600, 1024])
+def test_device_cholesky_is_bitwise_the_host_one(engine, oracle, N):
+    """mcr_device_transform: left-looking Cholesky, one thread per row, inner products accumulated in the host routine's order
+    with separate roundings -> the SAME bits as mcr_build_transform (and the oracle for the sizes it covers)."""
+    if N == 15:
+        g = np.load(GOLD / "pyref_n15.npz")
+        Sigma = g["Sigma"]
+    else:
+        Sigma = synthetic_model(N).Sigma
+    for mode in (api.TRANSFORM_LOWER, api.TRANSFORM_GSL_FULL):
+        A_dev = engine.device_transform(Sigma, mode)
+        np.testing.assert_array_equal(A_dev, api.build_transform(Sigma, mode))
+        if N <= 50:
+            np.testing.assert_array_equal(A_dev, oracle.transform(Sigma, mode))
+    with pytest.raises(api.McrError, match="not positive definite"):
+        engine.device_transform(-np.eye(5))
+
+
+@pytest.mark.parametrize("T,N", [(2800, 15), (1500, 600), (33, 70)])
+def test_device_moments_match_numpy(engine, T, N):
+    """mcr_device_moments = train.mean(), train.cov() of the reference's preprocessing (preprocessing_stats.py:18,21; ddof = 1).
+    Different summation order than numpy's: 1e-12 relative to the scale of the entries."""
+    rng = np.random.default_rng(T + N)
+    m = synthetic_model(N)
+    L = np.linalg.cholesky(m.Sigma)
+    X = m.mu + rng.standard_normal((T, N)) @ L.T
+    mu, Sigma = engine.device_moments(X)
+    np.testing.assert_allclose(mu, X.mean(axis=0), rtol=0, atol=1e-15 + 1e-13 * np.abs(X).max())
+    ref = np.cov(X, rowvar=False, ddof=1)
+    np.testing.assert_allclose(Sigma, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+    np.testing.assert_array_equal(Sigma, Sigma.T)
+    if T > N:   # full rank: the estimated model runs end to end
+        A = engine.device_transform(Sigma)
+        engine.upload_model(mu, A, a_is_lower=True)
+        r = engine.run(100_000, 67, m.x, m.k)
+        x = engine.run(100_000, 67, m.x, m.k, kernel=api.KERNEL_EXACT)
+        assert (r.count, r.sum_S) == (x.count, x.sum_S)
+
+
+@pytest.mark.skipif(not (PKG / "libmcr_b200_model.so").exists(), reason="plugin not built")
+def test_plugin_device_cholesky_option(monkeypatch):
+    """MCR_DEVICE_CHOLESKY=1 through get_cuda_model: identical results (the factor is bitwise the host's)."""
+    plugin = C.CDLL(str(PKG / "libmcr_b200_model.so"))
+    m = synthetic_model(100)
+    monkeypatch.setenv("MCR_S_VALUES", "1")
+    a = oracle_lib.run_model_struct(plugin.get_cuda_model, m.mu, m.Sigma, m.k, m.x, 300_000, 67)
+    monkeypatch.setenv("MCR_DEVICE_CHOLESKY", "1")
+    b = oracle_lib.run_model_struct(plugin.get_cuda_model, m.mu, m.Sigma, m.k, m.x, 300_000, 67)
+    assert a["rc"] == 0 and b["rc"] == 0 and a["count"] == b["count"]
+    np.testing.assert_array_equal(a["S_values"], b["S_values"])

@@ -12,7 +12,7 @@ obj=$out/obj
 mkdir -p "$obj"
 flags="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $*"
 pids=()
-for f in mcr_api mcr_host mcr_exact mcr_tc mcr_wide mcr_stream; do
+for f in mcr_api mcr_host mcr_exact mcr_tc mcr_wide mcr_stream mcr_stats; do
   nvcc $flags -c "$pkg/csrc/$f.cu" -o "$obj/$f.o" & pids+=($!)
 done
 for g in 0 1 2 3 4 5 6 7; do
