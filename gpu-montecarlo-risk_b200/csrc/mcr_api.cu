@@ -321,10 +321,9 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
     plan->slab = false;
     plan->rows = e->N + (plan->portfolio ? 1 : 0);
     if (plan->portfolio && normals) return fail("portfolio outputs are not available with supplied normals");
-    if ((plan->rows > tc_max_n() || normals) && (want == MCR_KERNEL_TENSOR || (want == MCR_KERNEL_AUTO && plan->rows > tc_max_n())) &&
-        stream_supported(e->N, plan->portfolio ? 1 : 0)) {
-        // more accumulator rows than the tile kernel holds (N > 128, or N = 128 plus the portfolio row), and every supplied-normals
-        // run that asks for the tensor path: the streamed kernel (mcr_stream.cu).  The two round-1 kernels stay selectable for A/B
+    if (plan->rows > tc_max_n() && (want == MCR_KERNEL_TENSOR || want == MCR_KERNEL_AUTO) && stream_supported(e->N, plan->portfolio ? 1 : 0)) {
+        // more accumulator rows than the tile kernel holds (N > 128, or N = 128 plus the portfolio row), generated or supplied
+        // normals: the streamed kernel (mcr_stream.cu).  The two round-1 kernels stay selectable for A/B
         // runs: MCR_LARGE_N=slab|wide (generated normals, no portfolio outputs).
         static const int forced = [] { const char* v = getenv("MCR_LARGE_N"); return !v ? 0 : !strcmp(v, "slab") ? 1 : !strcmp(v, "wide") ? 2 : 0; }();
         plan->kernel = MCR_KERNEL_TENSOR;
@@ -334,7 +333,7 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
         else { plan->stream = true; plan->NT = (plan->rows + 15) & ~15; }
         return 0;
     }
-    const bool tc_ok = !normals && tc_supported(plan->rows);
+    const bool tc_ok = tc_supported(plan->rows);   // (supplied normals: the tile kernel's supplied-normals instantiation, on request)
     if (plan->portfolio) {
         if (want != MCR_KERNEL_AUTO && want != MCR_KERNEL_TENSOR) return fail("portfolio outputs are produced by the tensor-core kernel only");
         if (!tc_ok) return fail("portfolio outputs: N=%d is outside the tensor kernels' range", e->N);
@@ -343,7 +342,7 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
     }
     if (want == MCR_KERNEL_TENSOR) {
         if (!tc_ok) return fail("tensor-core kernel covers N <= %d in this build (N=%d)", tc_max_n(), e->N);
-        plan->kernel = MCR_KERNEL_TENSOR; plan->NT = tc_padded_n(plan->rows);
+        plan->kernel = MCR_KERNEL_TENSOR; plan->NT = normals ? tc_supplied_padded_n() : tc_padded_n(plan->rows);
         return 0;
     }
     const int v = find_variant(e->N, e->lower, normals);
@@ -351,7 +350,7 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
     // tensor-core kernel above that (the FFMA kernel then stalls on constant-cache misses).  Measured
     // crossover on B200: N = 32 FFMA 2.3e10 vs tensor 2.1e10 sims/s, N = 40 1.6e10 vs 1.7e10
     // (profiles/r01_sweep_ffma_vs_tensor.log)
-    if (want == MCR_KERNEL_AUTO && tc_ok && (e->N >= auto_tc_min_n() || v < 0)) {
+    if (want == MCR_KERNEL_AUTO && tc_ok && !normals && (e->N >= auto_tc_min_n() || v < 0)) {
         plan->kernel = MCR_KERNEL_TENSOR; plan->NT = tc_padded_n(plan->rows);
         return 0;
     }
@@ -492,7 +491,9 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         // split, swizzled transform image (depends on x through the constant column): rebuilt only when
         // the model or x changed
         const int rows = plan.rows;
-        const size_t bytes = tc_image_bytes(rows);
+        const bool sup = dZ != nullptr;   // the supplied-normals instantiation: one shape (128 rows, 3 K-blocks), its own image
+        const size_t bytes = sup ? tc_supplied_image_bytes() : tc_image_bytes(rows);
+        const int nout = sup ? tc_supplied_padded_n() : tc_padded_n(rows);
         if (e->tc_image_cap < bytes) {
             cudaFree(e->d_tc_image); e->d_tc_image = nullptr; e->tc_image_cap = 0;
             MCR_CUDA(cudaMalloc(&e->d_tc_image, bytes));
@@ -508,16 +509,17 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             tl.port_x = opt->portfolio_loss_threshold;
             tl.port_acc = e->d_port_acc; tl.port_hist = e->d_port_hist; tl.port_hist_sum = e->d_port_hist_sum;
         }
-        const uint64_t image_key = e->gen * 2 + (plan.portfolio ? 1 : 0);
+        const uint64_t image_key = e->gen * 4 + (plan.portfolio ? 1 : 0) + (sup ? 2 : 0);
         if (e->tc_gen != image_key || e->tc_x != x || plan.portfolio) {
             e->tc_host_image.resize(bytes);
-            e->tc_row_scale.assign(tc_padded_n(rows), 1.0);
-            tc_build(N, rows, e->A.data(), c.data(), plan.portfolio ? port_row.data() : nullptr, e->tc_host_image.data(), e->tc_row_scale.data());
+            e->tc_row_scale.assign(nout, 1.0);
+            if (sup) tc_supplied_build(N, e->A.data(), c.data(), e->tc_host_image.data(), e->tc_row_scale.data());
+            else tc_build(N, rows, e->A.data(), c.data(), plan.portfolio ? port_row.data() : nullptr, e->tc_host_image.data(), e->tc_row_scale.data());
             MCR_CUDA(cudaStreamSynchronize(s));   // a previous run may still read the old image
             MCR_CUDA(cudaMemcpyAsync(e->d_tc_image, e->tc_host_image.data(), bytes, cudaMemcpyHostToDevice, s));
             e->tc_gen = image_key; e->tc_x = x;
         }
-        if (plan.portfolio) tl.port_scale = e->tc_row_scale[tc_padded_n(rows) - 1];
+        if (plan.portfolio) tl.port_scale = e->tc_row_scale[nout - 1];
         // Guard band, in accumulator units (accumulator i = s_i (R_i + x), s_i the row's power-of-two scale).  fp16x3: each
         // operand is hi + lo with relative residual 2^-22 (plus fp16-subnormal rounding of tiny z_lo, absolute 2^-25 per
         // normal), the lo*lo product is dropped, and the tensor core accumulates in fp32 over 12*KB MMA instructions: budget
@@ -536,14 +538,15 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         tl.delta_rel = plan.recheck ? band_scale * 2.0 * gamma * rowabs_max : 0.0;
         tl.delta_abs = plan.recheck ? band_scale * 2.0 * gamma * cabs_max + 1e-30 : 0.0;
         int bps = 0;
-        MCR_CUDA(tc_occupancy(plan.rows, plan.portfolio, &bps));
+        MCR_CUDA(sup ? tc_supplied_occupancy(&bps) : tc_occupancy(plan.rows, plan.portfolio, &bps));
         if (bps < 1) return fail("tensor-core kernel for N=%d%s does not fit one SM's shared memory", N, plan.portfolio ? " with the portfolio histogram" : "");
         if (const char* ov = getenv("MCR_TC_CTAS_PER_SM")) { if (atoi(ov) > 0) bps = atoi(ov); }  // tuning override
         tc_grid_full = std::min(sms * bps, MAX_GRID);
-        mma_flops = 3.0 * 2.0 * tc_padded_n(rows) * (64.0 * ((rows + 64) / 64)) * 1.0;   // 3 passes over the padded NOUT x K tile (K covers N + 1 columns)
+        mma_flops = sup ? 3.0 * 2.0 * 128.0 * 192.0 : 3.0 * 2.0 * tc_padded_n(rows) * (64.0 * ((rows + 64) / 64));   // 3 passes over the padded NOUT x K tile (K covers N + 1 columns)
         tl.key0 = key0; tl.key1 = key1; tl.k = k; tl.d_image = e->d_tc_image;
         tl.flag_list = e->d_flag_list; tl.flag_count = e->d_flag_count; tl.flag_cap = FLAG_CAP;
-        tl.pair_list = plan.recheck ? e->d_pair_list : nullptr; tl.pair_count = e->d_pair_count; tl.pair_cap = PAIR_CAP;
+        // (supplied normals: exact_pairs_kernel re-derives its normals from Philox, so every near-threshold trial takes the fp64 kernel)
+        tl.pair_list = (plan.recheck && !sup) ? e->d_pair_list : nullptr; tl.pair_count = e->d_pair_count; tl.pair_cap = PAIR_CAP;
         tl.block_partials = e->d_block_partials;
     }
 
@@ -792,7 +795,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             fin.block_partials = e->d_block_partials; fin.n_blocks = wide_grid(m, N, e->num_sms);
             fin.flag_count = e->d_flag_count; fin.flag_cap = FLAG_CAP;
         } else if (plan.kernel == MCR_KERNEL_TENSOR) {
-            tl.M = m; tl.path_offset = path_offset + done; tl.S_out = xp.S_out;
+            tl.M = m; tl.path_offset = path_offset + done; tl.S_out = xp.S_out; tl.d_Z = xp.Z;
             const uint64_t tiles = (m + 127) / 128;
             const int grid = (int)std::min<uint64_t>((uint64_t)tc_grid_full, tiles);
             const bool timed = e->n_timed < MAX_TIMED_CHUNKS;

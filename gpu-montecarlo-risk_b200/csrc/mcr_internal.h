@@ -111,7 +111,8 @@ struct TcLaunch {
     uint32_t key0, key1;
     int32_t k;
     double delta_rel, delta_abs; // guard band = delta_rel * max_j|z_j| + delta_abs, in accumulator units (row scales applied)
-    const void* d_image;        // device copy of the split, swizzled transform image (tc_build)
+    const void* d_image;        // device copy of the split, swizzled transform image (tc_build / tc_supplied_build)
+    const double* d_Z;          // supplied normals (M x N fp64, chunk-relative): the supplied-normals instantiation runs; else nullptr
     int32_t* S_out;
     uint32_t* flag_list;
     uint32_t* flag_count;
@@ -139,6 +140,11 @@ int tc_padded_n(int rows);
 void tc_build(int N, int rows, const double* A, const double* c, const double* port_row, uint8_t* image, double* row_scale);
 double tc_z_factor();   // what tc_build multiplies the transform columns by (the generator's folded sqrt(2 ln 2), or 1)
 cudaError_t tc_occupancy(int rows, bool portfolio, int* blocks_per_sm);
+// the supplied-normals instantiation of the tile kernel: one shape (128 rows, 3 K-blocks) for every N <= 128
+size_t tc_supplied_image_bytes();
+int tc_supplied_padded_n();
+void tc_supplied_build(int N, const double* A, const double* c, uint8_t* image, double* row_scale /* 128, out */);
+cudaError_t tc_supplied_occupancy(int* blocks_per_sm);
 cudaError_t tc_launch(int N, int rows, const TcLaunch& l, int grid, cudaStream_t s);
 
 // ---- tensor-core row-slab path for N > 128 (mcr_tc.cu) --------------------------------------------

@@ -278,6 +278,11 @@ __global__ void __launch_bounds__(256) slab_count_kernel(uint64_t M, const uint1
     }
 }
 
+static const TcVariant* tc_supplied() {
+    static const TcVariant v = tc_variant_inst<TC_SUPPLIED_INST>();
+    return &v;
+}
+
 // smallest instantiation with nout >= N and 64 * kb >= N + 1
 static const TcVariant* tc_find(int N) {
     static const TcVariant table[TC_VARIANTS] = {
@@ -292,6 +297,12 @@ static const TcVariant* tc_find(int N) {
 int tc_max_n() { return 128; }
 
 bool tc_supported(int rows) { return tc_find(rows) != nullptr; }
+
+// ---- the supplied-normals instantiation (one shape for every N <= 128) ----
+size_t tc_supplied_image_bytes() { return tc_supplied()->image_bytes; }
+int tc_supplied_padded_n() { return tc_supplied()->nout; }
+void tc_supplied_build(int N, const double* A, const double* c, uint8_t* image, double* row_scale) { tc_supplied()->build(A, c, N, nullptr, image, row_scale); }
+cudaError_t tc_supplied_occupancy(int* bps) { return tc_supplied()->occupancy(bps, false); }
 
 size_t tc_image_bytes(int rows) { const TcVariant* v = tc_find(rows); return v ? v->image_bytes : 0; }
 
@@ -321,7 +332,8 @@ cudaError_t tc_launch(int N, int rows, const TcLaunch& l, int grid, cudaStream_t
         p.tail_mul[q] = col < N ? 1.0f : 0.0f;
         p.tail_add[q] = col == N ? 1.0f : 0.0f;
     }
-    return tc_find(rows)->launch(p, grid, s);
+    p.Z = l.d_Z;
+    return (l.d_Z ? tc_supplied() : tc_find(rows))->launch(p, grid, s);
 }
 
 // ---- slab path host side ---------------------------------------------------------------------------------

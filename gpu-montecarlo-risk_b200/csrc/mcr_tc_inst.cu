@@ -7,10 +7,18 @@
 
 namespace mcr {
 
+#if MCR_TC_INST == 10   // = TC_SUPPLIED_INST: the kernel fed with the caller's normals
+static_assert(MCR_TC_INST == TC_SUPPLIED_INST, "supplied-normals instantiation index");
+template <>
+TcVariant tc_variant_inst<MCR_TC_INST>() {
+    return tc_variant<TC_SUPPLIED_NOUT, TC_SUPPLIED_KB, tc_groups(TC_SUPPLIED_NOUT, TC_SUPPLIED_KB), true>();
+}
+#else
 template <>
 TcVariant tc_variant_inst<MCR_TC_INST>() {
     constexpr int NOUT = TC_VARIANT_NOUT[MCR_TC_INST], KB = TC_VARIANT_KB[MCR_TC_INST];
     return tc_variant<NOUT, KB, tc_groups(NOUT, KB)>();
 }
+#endif
 
 }  // namespace mcr

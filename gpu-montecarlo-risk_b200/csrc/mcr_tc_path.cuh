@@ -46,6 +46,7 @@ struct TcParams {
     int32_t k, N;
     float delta_rel, delta_abs;   // guard band = delta_rel * max_j |z_j| + delta_abs (0, 0 disables the recheck)
     const uint4* B_image;   // global: [Bhi image | Blo image], each KB * NOUT * 128 bytes
+    const double* Z;        // SUPPLIED instantiation: the caller's normals, M x N fp64 row-major (chunk-relative)
     int32_t* S_out;
     uint32_t* flag_list;
     uint32_t* flag_count;
@@ -86,9 +87,23 @@ constexpr int TC_UNROLL = MCR_TC_UNROLL;  // 8-normal chunks in flight per gener
 constexpr bool TC_FOLD = MCR_TC_FOLD != 0;
 constexpr double TC_Z_FACTOR = TC_FOLD ? BOX_MULLER_S : 1.0;   // what the transform columns 0..N-1 are multiplied by
 
-// NB Philox blocks b.. of the path -> 4 NB normals (only LAST_NORMALS of the last block), and the running bound on |z|
-template <int NB, int LAST_NORMALS = 4>
-__device__ __forceinline__ void gen_blocks(const PhiloxPath& rng, uint32_t b, const PhiloxKeys& K, float* z, float& zbound) {
+// NB Philox blocks b.. of the path -> 4 NB normals (only LAST_NORMALS of the last block), and the running bound on |z|.
+// SUPPLIED: the 4 NB normals of columns 4 b .. come from the caller's fp64 row instead (zrow = nullptr for a trial past the end):
+// parity mode 1 "fed identical pre-generated normals through the interface" for this kernel.
+template <int NB, int LAST_NORMALS = 4, bool SUPPLIED = false>
+__device__ __forceinline__ void gen_blocks(const PhiloxPath& rng, uint32_t b, const PhiloxKeys& K, float* z, float& zbound,
+                                           const double* zrow = nullptr, int ncols = 0) {
+    if (SUPPLIED) {
+#pragma unroll
+        for (int q = 0; q < 4 * NB; ++q) {
+            const int col = 4 * (int)b + q;
+            float v = (zrow != nullptr && col < ncols) ? __double2float_rn(zrow[col]) : 0.0f;
+            if (TC_FOLD) v = __fmul_rn(v, (float)(1.0 / BOX_MULLER_S));   // the image carries the factor back (one more fp32 rounding, inside the band)
+            z[q] = v;
+            zbound = fmaxf(zbound, fabsf(v));
+        }
+        return;
+    }
     if (TC_FOLD) {
         rng.normals_multi_raw<NB, LAST_NORMALS>(b, K, z, zbound);
     } else {   // zbound is tracked by store_chunk<true>
@@ -119,7 +134,7 @@ __device__ __forceinline__ void gen_blocks(const PhiloxPath& rng, uint32_t b, co
 //     overwrites it is issued, so a single region per group is enough.
 // No group ever waits for another one (an earlier version served all groups from one MMA warp in
 // round-robin order: about 10 % of the warp samples sat in that coupling).
-template <int NOUT, int KB, int GROUPS>
+template <int NOUT, int KB, int GROUPS, bool SUPPLIED = false>
 __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams p) {
     using namespace tc;
     constexpr uint32_t SLOT_BYTES = 2 * TILE_M * 128;   // one K-block of Z: hi then lo
@@ -272,6 +287,7 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
             const uint64_t path = p.path_offset + i;
             PhiloxPath rng;
             rng.init((uint32_t)path, (uint32_t)(path >> 32), p.key1);
+            const double* zrow = (SUPPLIED && i < p.M) ? p.Z + (size_t)i * (size_t)p.N : nullptr;
             float zmax = 0.0f;
 #pragma unroll 1
             for (int kb = 0; kb < KB; ++kb, ++u) {
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
                 int c8 = c_begin;
                 for (; c8 + TC_UNROLL <= min(n_full, c_begin + 8); c8 += TC_UNROLL) {
                     float z[8 * TC_UNROLL];
-                    gen_blocks<2 * TC_UNROLL>(rng, (uint32_t)(2 * c8), p.keys, z, zmax);
+                    gen_blocks<2 * TC_UNROLL, 4, SUPPLIED>(rng, (uint32_t)(2 * c8), p.keys, z, zmax, zrow, p.N);
                     acquire();
 #pragma unroll
                     for (int w = 0; w < TC_UNROLL; ++w) {
@@ -298,7 +314,7 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
                 }
                 for (; c8 < min(n_full, c_begin + 8); ++c8) {
                     float z[8];
-                    gen_blocks<2>(rng, (uint32_t)(2 * c8), p.keys, z, zmax);
+                    gen_blocks<2, 4, SUPPLIED>(rng, (uint32_t)(2 * c8), p.keys, z, zmax, zrow, p.N);
                     acquire();
                     store_chunk<!TC_FOLD>(z, c8 - c_begin, zhi_row, zlo_row, r7s, zmax);
                 }
@@ -310,10 +326,10 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) tc_path_kernel(const TcParams
                     float z[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) z[q] = 0.0f;
-                    if (rem > 6) gen_blocks<2, 4>(rng, (uint32_t)(2 * n_full), p.keys, z, zmax);
-                    else if (rem > 4) gen_blocks<2, 2>(rng, (uint32_t)(2 * n_full), p.keys, z, zmax);
-                    else if (rem > 2) gen_blocks<1, 4>(rng, (uint32_t)(2 * n_full), p.keys, z, zmax);
-                    else if (rem > 0) gen_blocks<1, 2>(rng, (uint32_t)(2 * n_full), p.keys, z, zmax);
+                    if (rem > 6) gen_blocks<2, 4, SUPPLIED>(rng, (uint32_t)(2 * n_full), p.keys, z, zmax, zrow, p.N);
+                    else if (rem > 4) gen_blocks<2, 2, SUPPLIED>(rng, (uint32_t)(2 * n_full), p.keys, z, zmax, zrow, p.N);
+                    else if (rem > 2) gen_blocks<1, 4, SUPPLIED>(rng, (uint32_t)(2 * n_full), p.keys, z, zmax, zrow, p.N);
+                    else if (rem > 0) gen_blocks<1, 2, SUPPLIED>(rng, (uint32_t)(2 * n_full), p.keys, z, zmax, zrow, p.N);
 #pragma unroll
                     for (int q = 0; q < 8; ++q)   // mul/add are (1, 0) for the normals, (0, 1) for the constant 1 in column N, (0, 0) beyond:
                         z[q] = __fmaf_rn(z[q], p.tail_mul[q], p.tail_add[q]);   // exact; the 1 only widens zmax (never below 1)
@@ -428,34 +444,34 @@ static size_t tc_smem_bytes(bool portfolio) {
     return (size_t)GROUPS * 2 * tc::TILE_M * 128 + 2 * (size_t)KB * NOUT * 128 + 1024 + (portfolio ? 8 * (size_t)PORT_BINS : 0);
 }
 
-template <int NOUT, int KB, int GROUPS>
+template <int NOUT, int KB, int GROUPS, bool SUPPLIED = false>
 static cudaError_t tc_prepare(bool portfolio) {
     // opt in to the large dynamic shared memory and the largest carveout (several CTAs per SM overlap
     // each other's bubbles); both are per-device function attributes, cheap to set repeatedly
-    cudaError_t e = cudaFuncSetAttribute(tc_path_kernel<NOUT, KB, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tc_path_kernel<NOUT, KB, GROUPS, SUPPLIED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)tc_smem_bytes<NOUT, KB, GROUPS>(portfolio));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tc_path_kernel<NOUT, KB, GROUPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return cudaFuncSetAttribute(tc_path_kernel<NOUT, KB, GROUPS, SUPPLIED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-template <int NOUT, int KB, int GROUPS>
+template <int NOUT, int KB, int GROUPS, bool SUPPLIED = false>
 static cudaError_t tc_launch_impl(const TcParams& p, int grid, cudaStream_t s) {
-    cudaError_t e = tc_prepare<NOUT, KB, GROUPS>(p.portfolio != 0);
+    cudaError_t e = tc_prepare<NOUT, KB, GROUPS, SUPPLIED>(p.portfolio != 0);
     if (e != cudaSuccess) return e;
-    tc_path_kernel<NOUT, KB, GROUPS><<<grid, 128 * GROUPS, tc_smem_bytes<NOUT, KB, GROUPS>(p.portfolio != 0), s>>>(p);
+    tc_path_kernel<NOUT, KB, GROUPS, SUPPLIED><<<grid, 128 * GROUPS, tc_smem_bytes<NOUT, KB, GROUPS>(p.portfolio != 0), s>>>(p);
     return cudaGetLastError();
 }
 
 // CTAs that fit one SM.  Computed here because cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1
 // for this kernel although the hardware co-schedules more (measured: 4 CTAs/SM run 2.2x faster than 1):
 // shared memory, TMEM columns (512 per SM), threads and registers bound it.
-template <int NOUT, int KB, int GROUPS>
+template <int NOUT, int KB, int GROUPS, bool SUPPLIED = false>
 static cudaError_t tc_occupancy_impl(int* bps, bool portfolio) {
     if (tc_smem_bytes<NOUT, KB, GROUPS>(portfolio) > 227 * 1024) { *bps = 0; return cudaSuccess; }
-    cudaError_t e = tc_prepare<NOUT, KB, GROUPS>(portfolio);
+    cudaError_t e = tc_prepare<NOUT, KB, GROUPS, SUPPLIED>(portfolio);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa{};
-    e = cudaFuncGetAttributes(&fa, tc_path_kernel<NOUT, KB, GROUPS>);
+    e = cudaFuncGetAttributes(&fa, tc_path_kernel<NOUT, KB, GROUPS, SUPPLIED>);
     if (e != cudaSuccess) return e;
     int dev = 0, smem_sm = 0, regs_sm = 0;
     cudaGetDevice(&dev);
@@ -484,10 +500,10 @@ struct TcVariant {
     cudaError_t (*occupancy)(int*, bool);
 };
 
-template <int NOUT, int KB, int GROUPS>
+template <int NOUT, int KB, int GROUPS, bool SUPPLIED = false>
 static TcVariant tc_variant() {
-    return TcVariant{NOUT, KB, GROUPS, 2 * (size_t)KB * NOUT * 128, &tc_build_image<NOUT, KB>, &tc_launch_impl<NOUT, KB, GROUPS>,
-                     &tc_occupancy_impl<NOUT, KB, GROUPS>};
+    return TcVariant{NOUT, KB, GROUPS, 2 * (size_t)KB * NOUT * 128, &tc_build_image<NOUT, KB>, &tc_launch_impl<NOUT, KB, GROUPS, SUPPLIED>,
+                     &tc_occupancy_impl<NOUT, KB, GROUPS, SUPPLIED>};
 }
 
 // warpgroups per CTA: as many as the tuning default, TMEM (512 columns) and shared memory (227 KB) allow
@@ -503,5 +519,7 @@ constexpr int TC_VARIANTS = 10;
 constexpr int TC_VARIANT_NOUT[TC_VARIANTS] = {16, 32, 48, 64, 64, 80, 96, 112, 128, 128};
 constexpr int TC_VARIANT_KB[TC_VARIANTS] = {1, 1, 1, 1, 2, 2, 2, 2, 2, 3};
 template <int I> TcVariant tc_variant_inst();
+// the one supplied-normals instantiation (translation unit MCR_TC_INST = TC_VARIANTS): the widest shape, it covers every N <= 128
+constexpr int TC_SUPPLIED_INST = TC_VARIANTS, TC_SUPPLIED_NOUT = 128, TC_SUPPLIED_KB = 3;
 
 }  // namespace mcr

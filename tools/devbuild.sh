@@ -18,7 +18,7 @@ done
 for g in 0 1 2 3 4 5 6 7; do
   nvcc $flags -DMCR_INST_GROUP=$g -c "$pkg/csrc/mcr_ffma_inst.cu" -o "$obj/mcr_ffma_inst_$g.o" & pids+=($!)
 done
-for v in 0 1 2 3 4 5 6 7 8 9; do
+for v in 0 1 2 3 4 5 6 7 8 9 10; do
   nvcc $flags -DMCR_TC_INST=$v -c "$pkg/csrc/mcr_tc_inst.cu" -o "$obj/mcr_tc_inst_$v.o" & pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
