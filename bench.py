@@ -484,7 +484,7 @@ def main():
 
         configs.append(run_config("C3: EuroNext100 shape, N=100, 1e9 trials in total, strong-scaled", 100, 1_000_000_000, 3, 1, "strong"))
         configs.append(run_config("C4: Stoxx600 shape, N=600, 1e8 trials in total, tensor-core contraction", 600, 100_000_000, 3, 1, "strong"))
-        for n_assets in (16, 256, 1024):
+        for n_assets in (16, 32, 64, 128, 256, 512, 1024):
             configs.append(run_config(f"C5 (reduced sweep): N={n_assets}, 1e7 trials per GPU", n_assets, 10_000_000, 3, 1, "weak"))
         job.upload()   # back to the headline model for the legs below
 

@@ -162,11 +162,22 @@ __global__ void __launch_bounds__(128, MCR_MIN_BLOCKS) ffma_path_kernel(const Ff
             for (int pp = 0; pp < PPT; ++pp) {
                 if constexpr (FROM_NORMALS) {
                     const double* zrow = p.Z + (valid[pp] ? idx[pp] : i0) * (uint64_t)p.N;
+                    if ((p.N & 1) == 0 && (reinterpret_cast<uintptr_t>(p.Z) & 15) == 0 && 4 * b + 4 <= p.N) {
+                        // even N: every row starts 16-byte aligned, so the four normals of a block are two 16-byte loads
+                        // (the lanes of a warp read rows N * 8 bytes apart: the load unit, not HBM, bounds this mode)
+                        const double2 a = __ldg(reinterpret_cast<const double2*>(zrow + 4 * b));
+                        const double2 c = __ldg(reinterpret_cast<const double2*>(zrow + 4 * b + 2));
+                        z[pp][0] = __double2float_rn(a.x); z[pp][1] = __double2float_rn(a.y);
+                        z[pp][2] = __double2float_rn(c.x); z[pp][3] = __double2float_rn(c.y);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int j = 4 * b + q;
-                        z[pp][q] = (j < p.N) ? __double2float_rn(zrow[j]) : 0.0f;
-                        zmax[pp] = fmaxf(zmax[pp], fabsf(z[pp][q]));
+                        for (int q = 0; q < 4; ++q) zmax[pp] = fmaxf(zmax[pp], fabsf(z[pp][q]));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int j = 4 * b + q;
+                            z[pp][q] = (j < p.N) ? __double2float_rn(zrow[j]) : 0.0f;
+                            zmax[pp] = fmaxf(zmax[pp], fabsf(z[pp][q]));
+                        }
                     }
                 } else {
 #if MCR_ABLATE == 1   // tuning only: no RNG, normals replaced by a 2-instruction hash
