@@ -229,8 +229,9 @@ int stream_plan(int N, int port, bool lower, StreamPass* pass /* STREAM_MAX_PASS
 size_t stream_image_bytes(int N, int port, bool lower);
 double stream_mma_flops(int N, int port, bool lower);          // fp16 MMA flops issued per trial
 int stream_normals_per_trial(int N, int port, bool lower);     // normals generated per trial (passes re-derive the leading columns)
-// port_row: nullptr, or N + 1 values (w^T A, then w.mu).  row_scale: out, N (+ 1) entries
-void stream_build(int N, bool lower, const double* A, const double* c, const double* port_row, uint8_t* image, double* row_scale);
+// port_row: nullptr, or N + 1 values (w^T A, then w.mu).  supplied_order: the image for supplied-normals runs (no Z cache: every pass
+// visits its K-blocks in ascending order; generated runs take the cached K-blocks last).  row_scale: out, N (+ 1) entries
+void stream_build(int N, bool lower, const double* A, const double* c, const double* port_row, bool supplied_order, uint8_t* image, double* row_scale);
 int stream_grid(uint64_t M, int num_sms);
 cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s);
 

@@ -105,6 +105,20 @@ __host__ __device__ inline int stream_acol0(int r0, int kb, int lower) {
     const int a = lower ? 64 * kb - r0 : 0;
     return a > 0 ? a : 0;
 }
+// Order in which a pass visits its K-blocks: ascending by default.  MCR_STREAM_CACHED_LAST=1 (build option) makes a later pass take
+// the K-blocks it has to generate first (kcache, kcache + 1, ...) and the cached ones (0 .. kcache - 1) last - feeding a cached block
+// costs the generators nothing while its MMAs are the widest of the pass, so at the end of the pass the generators could already
+// produce the next tile.  Measured: 2 % SLOWER at N = 600 / 1000 (profiles/r02_stream_kernel_development.log), because the
+// incremental read-out of finished columns is lost in those passes; kept for A/B runs.
+#ifndef MCR_STREAM_CACHED_LAST
+#define MCR_STREAM_CACHED_LAST 0
+#endif
+__host__ __device__ inline int stream_kb(int ps, int step, int kbn, int kcache) {
+    if (!MCR_STREAM_CACHED_LAST || ps == 0 || kcache <= 0) return step;
+    return step < kbn - kcache ? kcache + step : step - (kbn - kcache);
+}
+__host__ __device__ inline bool stream_ascending(int ps, int kcache) { return !MCR_STREAM_CACHED_LAST || ps == 0 || kcache <= 0; }
+
 // an active width w <= 384 as one or two chunks (one transform piece and one MMA N each; <= 256, multiple of 16)
 __host__ __device__ inline int stream_n1(int w) { return w <= ST_CHUNK_MAX ? w : ((w / 2 + 15) & ~15); }
 
@@ -213,7 +227,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
         for (uint64_t n = 0; n < my_tiles; ++n) {
             for (int ps = 0; ps < NPASS; ++ps) {
                 const int r0 = p.pass[ps].r0, W = p.pass[ps].W, KBN = p.pass[ps].kbn;
-                for (int kb = -1; kb < KBN; ++kb, ++zu) {
+                for (int st = -1; st < KBN; ++st, ++zu) {
+                    const int kb = st < 0 ? -1 : stream_kb(ps, st, KBN, p.kcache);
                     const uint32_t slot = zu & 1u;
                     named_bar_sync(ST_BAR_SLOT + slot, ST_ALL);            // the Z slot is written (tcgen05.st waited for, fenced)
                     if (kb < 0) named_bar_sync(ST_BAR_ACC, ST_ALL);        // the previous pass has been read out of the accumulators
@@ -247,7 +262,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                                 else umma_commit(&s_bempty[rs]);
                                 if (last) {
                                     umma_commit(&s_zempty[slot]);
-                                    if (kb == KBN - 1) umma_commit(&s_done);
+                                    if (st == KBN - 1) umma_commit(&s_done);
                                 }
                             }
                             __syncwarp();
@@ -265,7 +280,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                 const uint8_t* src = p.image;
                 for (int ps = 0; ps < NPASS; ++ps) {
                     const int r0 = p.pass[ps].r0, W = p.pass[ps].W, KBN = p.pass[ps].kbn;
-                    for (int kb = -1; kb < KBN; ++kb) {
+                    for (int st = -1; st < KBN; ++st) {
+                        const int kb = st < 0 ? -1 : stream_kb(ps, st, KBN, p.kcache);
                         const int w = W - (kb < 0 ? 0 : stream_acol0(r0, kb, LOWER)), n1 = stream_n1(w), n2 = w - n1;
                         for (int half = 0; half < (kb < 0 ? 1 : 2); ++half)
                             for (int c = 0; c < (n2 > 0 ? 2 : 1); ++c, ++piece) {
@@ -440,7 +456,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                 const int KBN = p.pass[ps].kbn, kend = p.pass[ps].kend;
                 float zsq = ps > 0 ? zsq_cached : 0.0f;
 #pragma unroll 1
-                for (int kb = -1; kb < KBN; ++kb, ++zu) {
+                for (int st = -1; st < KBN; ++st, ++zu) {
+                    const int kb = st < 0 ? -1 : stream_kb(ps, st, KBN, KCACHE);
                     const uint32_t slot = zu & 1u;
                     const uint32_t zaddr = lane_addr + slot * ST_ZCOLS + (uint32_t)(8 * part);
                     uint32_t hv[8], lv[8];
@@ -502,7 +519,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                     // now, while the tensor core works on.  The end of the pass is then left with the last few columns: neither do the
                     // generators wait long for the tensor core to drain, nor the tensor core for the read-out.  (The previous pass
                     // is pending until this pass's K-block 0 has been queued: nothing is read early before kb = 2.)
-                    if (LOWER && kb >= 2) read_columns(ps, min(p.pass[ps].W, 64 * (kb - 1) - p.pass[ps].r0), false, i);
+                    if (LOWER && st >= 2 && stream_ascending(ps, KCACHE)) read_columns(ps, min(p.pass[ps].W, 64 * (st - 1) - p.pass[ps].r0), false, i);
                     if (kb >= 0) {
                         tmem_st8(zaddr, hv);
                         tmem_st8(zaddr + 32u, lv);
@@ -514,7 +531,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                     tc_fence_before();
                     named_bar_arrive(ST_BAR_SLOT + slot, ST_ALL);
                     // the previous pass is read out once this pass's constant slot and first K-block are queued for the tensor core
-                    if (kb == 0 && pending) {
+                    if (st == 0 && pending) {
                         epilogue(pend_ps, pend_zsq, pend_i, pend_ps == NPASS - 1, true);
                         pending = false;
                     }
@@ -615,7 +632,7 @@ static void put_half(uint8_t* piece, int r, int kk, __half v) { memcpy(piece + t
 // (stream_n1), each (rows) x 64 fp16 in the K-major 128-byte-swizzled operand layout; row i carries s_i A_ij (row_scale:
 // tc_row_scale), the constant piece s_i (mu_i + x) as hi (K column 0) and lo (K column 1); padded rows hold zeros and a large
 // positive constant
-void stream_build(int N, bool lower, const double* A, const double* c, const double* port_row, uint8_t* image, double* row_scale) {
+void stream_build(int N, bool lower, const double* A, const double* c, const double* port_row, bool supplied_order, uint8_t* image, double* row_scale) {
     StreamPass ps[STREAM_MAX_PASSES];
     const int port = port_row ? 1 : 0;
     const int np = stream_plan(N, port, lower, ps);
@@ -636,7 +653,9 @@ void stream_build(int N, bool lower, const double* A, const double* c, const dou
     uint8_t* out = image;
     for (int q = 0; q < np; ++q) {
         const int r0 = ps[q].r0, W = ps[q].W;
-        for (int kb = -1; kb < ps[q].kbn; ++kb) {
+        const int kcache = np > 1 ? std::min(ST_KCACHE_MAX, ps[0].kend / tc::KBLOCK) : 0;   // as stream_launch sets it (generated normals)
+        for (int st = -1; st < ps[q].kbn; ++st) {
+            const int kb = st < 0 ? -1 : stream_kb(q, st, ps[q].kbn, supplied_order ? 0 : kcache);
             const int a0 = kb < 0 ? 0 : stream_acol0(r0, kb, lower), w = W - a0, n1 = stream_n1(w);
             // piece of (half, chunk): halves outer, chunks inner, as the kernel consumes them
             uint8_t* piece[2][2] = {{out, out + (size_t)n1 * 128}, {out + (size_t)w * 128, out + (size_t)(w + n1) * 128}};
