@@ -35,6 +35,16 @@
 #ifndef MCR_MIN_BLOCKS
 #define MCR_MIN_BLOCKS 1
 #endif
+// 1: the transform is copied to shared memory once per block and streamed from there with 16-byte broadcast loads (every lane the
+// same address: one wavefront) instead of uniform constant loads.  The constant path sustains about one 16-byte load per 10 cycles
+// and SM sub-partition and misses its first-level cache once the transform exceeds ~2 KB; see DESIGN.md section 3.3.
+// Measured (round 2, profiles/r02_ffma_smem_transform.log): N = 16 / 32 / 50 are 5-7 % SLOWER from shared memory (1.81 / 4.42 / 9.42 ms
+// against 1.69 / 4.19 / 8.92 per 1e8 trials: a 16-byte LDS occupies the SM's one load/store path for 4 cycles whatever the
+// broadcast, which is no better than the constant path's rate), N = 100 is 36 % faster (the 40 KB transform thrashes the constant
+// caches) - but AUTO runs the tensor kernel from N = 36.  Off by default.
+#ifndef MCR_FFMA_SMEM
+#define MCR_FFMA_SMEM 0
+#endif
 #include "mcr_internal.h"
 #include "mcr_rng.cuh"
 
@@ -94,6 +104,10 @@ __device__ __forceinline__ uint64_t ffma2_ordered(uint64_t a, uint64_t b, uint64
 __device__ __forceinline__ void ldc128(uint64_t const_addr, uint64_t& a, uint64_t& b) {
     asm volatile("ld.const.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(const_addr));
 }
+// 16 bytes from shared memory (address in the shared window), same contract
+__device__ __forceinline__ void lds128(uint32_t smem_addr, uint64_t& a, uint64_t& b) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(smem_addr));
+}
 // prefetch the line holding a (generic) constant-memory address into the uniform/constant cache
 __device__ __forceinline__ void prefetch_const(const void* generic_ptr) {
     asm volatile("prefetchu.L1 [%0];" :: "l"(generic_ptr));
@@ -115,6 +129,15 @@ __global__ void __launch_bounds__(128, MCR_MIN_BLOCKS) ffma_path_kernel(const Ff
     // .const-space byte addresses (ld.const takes those, not generic pointers)
     const uint64_t cA_const = (uint64_t)__cvta_generic_to_constant(cA2);
     const uint64_t cC_const = (uint64_t)__cvta_generic_to_constant(cC2);
+#if MCR_FFMA_SMEM
+    __shared__ __align__(16) float2 sA2[L::n_pairs + 2];
+    for (int t = threadIdx.x; t < L::n_pairs; t += blockDim.x) sA2[t] = cA2[t];
+    __syncthreads();
+    const uint32_t sA_addr = (uint32_t)__cvta_generic_to_shared(sA2);
+#define MCR_LOAD_A(e_, a_, b_) lds128(sA_addr + 16u * (uint32_t)(e_), a_, b_)
+#else
+#define MCR_LOAD_A(e_, a_, b_) ldc128(cA_const + 16 * (e_), a_, b_)
+#endif
 
     // One thread carries PPT trials at a time (trial indices i0, i0 + T, ...): every 16-byte uniform
     // load of the transform then feeds 2 * PPT packed FMAs instead of 2.  The uniform constant-load
@@ -149,7 +172,7 @@ __global__ void __launch_bounds__(128, MCR_MIN_BLOCKS) ffma_path_kernel(const Ff
         // pipeline prologue: the first DEPTH couples of the transform stream
         uint64_t pipe[DEPTH][2];
 #pragma unroll
-        for (int e = 0; e < DEPTH; ++e) ldc128(cA_const + 16 * (e < L::n_pairs / 2 ? e : 0), pipe[e][0], pipe[e][1]);
+        for (int e = 0; e < DEPTH; ++e) MCR_LOAD_A((e < L::n_pairs / 2 ? e : 0), pipe[e][0], pipe[e][1]);
 
         float zmax[PPT];
 #pragma unroll
@@ -213,7 +236,7 @@ __global__ void __launch_bounds__(128, MCR_MIN_BLOCKS) ffma_path_kernel(const Ff
                             if constexpr (m + 1 < H) acc[pp][m + 1] = ffma2_ordered(a1, zz[pp], acc[pp][m + 1]);
                         }
                         if constexpr (e + DEPTH < L::n_pairs / 2)
-                            ldc128(cA_const + 16 * (e + DEPTH), pipe[e % DEPTH][0], pipe[e % DEPTH][1]);
+                            MCR_LOAD_A((e + DEPTH), pipe[e % DEPTH][0], pipe[e % DEPTH][1]);
                         // The SM's first-level constant cache is far smaller than the transform (5 KB at
                         // N = 50), so the stream misses to the GPC-level constant cache once per line and
                         // the (loosely lock-stepped) warps of the SM all wait on that miss.  Optionally touch

@@ -21,15 +21,16 @@ def child(N, M):
     e = api.Engine(0)
     e.upload_sigma(m.mu, m.Sigma)
     nr = bool(os.environ.get("MCR_TUNE_NORECHECK"))   # ablated kernels produce garbage decisions
+    kern = {"auto": api.KERNEL_AUTO, "ffma": api.KERNEL_FFMA, "tensor": api.KERNEL_TENSOR}[os.environ.get("MCR_TUNE_KERNEL", "auto")]
     for _ in range(3):
-        r = e.run(M, 67, m.x, m.k, no_recheck=nr)
+        r = e.run(M, 67, m.x, m.k, no_recheck=nr, kernel=kern)
     ks, tot = [], []
     for _ in range(7):
-        r = e.run(M, 67, m.x, m.k, no_recheck=nr)
+        r = e.run(M, 67, m.x, m.k, no_recheck=nr, kernel=kern)
         avg, launches = e.last_main_kernel_ms()   # average per launch; a run is split into chunks
         ks.append(avg * launches)
         tot.append(r.device_ms)
-    raw = e.run(M, 67, m.x, m.k, no_recheck=True)
+    raw = e.run(M, 67, m.x, m.k, no_recheck=True, kernel=kern)
     kms = float(np.median(ks))
     F = N * N + 3 * N
     print(json.dumps({"kernel_ms": kms, "run_ms": float(np.median(tot)), "norecheck_run_ms": raw.device_ms,
