@@ -46,6 +46,31 @@ namespace mcr {
 #define MCR_STREAM_ABLATE 0
 #endif
 
+// tuning only: -DMCR_STREAM_TRACE=1 records clock64 time stamps of CTA 0 (generator warps 0 and 12, the MMA warp, the loader) into
+// g_stream_trace, read back with mcr_stream_trace_dump (tools/stream_trace.py prints a timeline of one tile)
+#ifndef MCR_STREAM_TRACE
+#define MCR_STREAM_TRACE 0
+#endif
+#if MCR_STREAM_TRACE
+constexpr int TRACE_ROLES = 4, TRACE_CAP = 16384;
+__device__ unsigned long long g_stream_trace[TRACE_ROLES * TRACE_CAP];
+__device__ unsigned int g_stream_trace_n[TRACE_ROLES];
+// the event index lives in a register of the recording thread (trace_i, declared per role): recording an event is one clock read
+// and one fire-and-forget store, nothing is loaded
+__device__ __forceinline__ void trace_event(int role, uint32_t& i, uint32_t tag, uint32_t val) {
+    if (i < TRACE_CAP) {
+        g_stream_trace[role * TRACE_CAP + i] = ((unsigned long long)tag << 56) | ((unsigned long long)(val & 0xFFFFu) << 40) | ((unsigned long long)clock64() & 0xFFFFFFFFFFull);
+        ++i;
+        g_stream_trace_n[role] = i;
+    }
+}
+#define ST_TRACE(role, tag, val) do { if (blockIdx.x == 0 && lane == 0) trace_event(role, trace_i, tag, (uint32_t)(val)); } while (0)
+#define ST_TRACE_DECL uint32_t trace_i = 0;
+#else
+#define ST_TRACE(role, tag, val) do { } while (0)
+#define ST_TRACE_DECL
+#endif
+
 constexpr int ST_WMAX = STREAM_WMAX;                 // accumulator columns = transform rows per pass
 constexpr int ST_ZSLOTS = 2;
 constexpr int ST_ZCOLS = 64;                         // TMEM columns of a Z slot: 32 (hi pairs) + 32 (lo pairs)
@@ -217,6 +242,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
     // whose trials (i >= M) are generated and multiplied like any other but never counted
     const uint64_t n_tiles = (p.M + TILE_M - 1) / TILE_M;
     const uint64_t my_tiles = (n_tiles + gridDim.x - 1) / gridDim.x;
+    ST_TRACE_DECL
     const int NPASS = p.npass, LOWER = p.lower;
 
     if (warp == ST_MMA_WARP) {
@@ -230,8 +256,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                 for (int st = -1; st < KBN; ++st, ++zu) {
                     const int kb = st < 0 ? -1 : stream_kb(ps, st, KBN, p.kcache);
                     const uint32_t slot = zu & 1u;
+                    ST_TRACE(2, 1, kb);                                    // waiting for the Z slot
                     named_bar_sync(ST_BAR_SLOT + slot, ST_ALL);            // the Z slot is written (tcgen05.st waited for, fenced)
-                    if (kb < 0) named_bar_sync(ST_BAR_ACC, ST_ALL);        // the previous pass has been read out of the accumulators
+                    ST_TRACE(2, 2, kb);
+                    if (kb < 0) { named_bar_sync(ST_BAR_ACC, ST_ALL); ST_TRACE(2, 3, kb); }   // the previous pass has been read out of the accumulators
                     const int acol0 = kb < 0 ? 0 : stream_acol0(r0, kb, LOWER);
                     const int w = W - acol0, n1 = stream_n1(w), n2 = w - n1;
                     const uint32_t a_hi = tmem_base + slot * ST_ZCOLS, a_lo = a_hi + 32u;
@@ -242,6 +270,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                             const uint32_t id = make_idesc(c ? n2 : n1);
                             const bool last = half == (kb < 0 ? 0 : 1) && c == (n2 > 0 ? 1 : 0);
                             mbar_wait<20>(&s_bfull[rs], rphase);
+                            ST_TRACE(2, 4, kb);                            // piece arrived
                             if (elect_one()) {
                                 tc_fence_after();
                                 const uint64_t b = make_desc(smem_u32(s_ring + rs * ST_PIECE_MAX));
@@ -266,6 +295,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                                 }
                             }
                             __syncwarp();
+                            ST_TRACE(2, 5, kb);                            // MMAs of the piece issued
                             next_piece();
                         }
                     }
@@ -288,6 +318,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                                 const uint32_t bytes = (uint32_t)(c ? n2 : n1) * 128u;
                                 // slot rs has been consumed by every CTA of the pair (their commits arrive on both copies of s_bempty)
                                 if (piece >= (uint32_t)RING) mbar_wait<20>(&s_bempty[rs], rphase ^ 1u);
+                                ST_TRACE(3, 1, kb);                        // ring slot free, copy issued
                                 if ((MCR_STREAM_ABLATE & 1) && piece >= (uint32_t)RING) {
                                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_bfull[rs])) : "memory");
                                 } else {
@@ -379,6 +410,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
             mbar_wait<64>(&s_done, done_parity);
             done_parity ^= 1u;
             tc_fence_after();
+            if (warp == 0) ST_TRACE(0, 7, ps);                                                        // the pass's MMAs are complete
             const int r0 = p.pass[ps].r0;
             read_columns(ps, p.pass[ps].W, true, i);
             uint32_t S = S_pass;
@@ -460,6 +492,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                     const int kb = st < 0 ? -1 : stream_kb(ps, st, KBN, KCACHE);
                     const uint32_t slot = zu & 1u;
                     const uint32_t zaddr = lane_addr + slot * ST_ZCOLS + (uint32_t)(8 * part);
+                    if (warp == 0) ST_TRACE(0, 1, kb); else if (warp == 12) ST_TRACE(1, 1, kb);      // step begins
                     uint32_t hv[8], lv[8];
                     if (kb >= 0) {
                         const int col0 = KBLOCK * kb + 16 * part;
@@ -512,8 +545,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                         }
                     }
                     // stay within ST_ZSLOTS slots of the tensor core
+                    if (warp == 0) ST_TRACE(0, 2, kb); else if (warp == 12) ST_TRACE(1, 2, kb);      // normals ready, waiting for the slot
                     if (zu >= (uint32_t)ST_ZSLOTS) mbar_wait<64>(&s_zempty[slot], ((zu / ST_ZSLOTS) - 1u) & 1u);
                     tc_fence_after();
+                    if (warp == 0) ST_TRACE(0, 3, kb); else if (warp == 12) ST_TRACE(1, 3, kb);      // slot free
                     // The slot is free, so the MMAs of this pass's K-block kb - 2 are complete; with a lower-triangular transform the
                     // K-blocks after it only touch the rows >= 64 (kb - 1), so the accumulator columns below that are final and are read
                     // now, while the tensor core works on.  The end of the pass is then left with the last few columns: neither do the
@@ -530,10 +565,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                     tmem_store_wait();
                     tc_fence_before();
                     named_bar_arrive(ST_BAR_SLOT + slot, ST_ALL);
+                    if (warp == 0) ST_TRACE(0, 4, kb); else if (warp == 12) ST_TRACE(1, 4, kb);      // handed over
                     // the previous pass is read out once this pass's constant slot and first K-block are queued for the tensor core
                     if (st == 0 && pending) {
+                        if (warp == 0) ST_TRACE(0, 5, pend_ps);
                         epilogue(pend_ps, pend_zsq, pend_i, pend_ps == NPASS - 1, true);
                         pending = false;
+                        if (warp == 0) ST_TRACE(0, 6, pend_ps);
                     }
                 }
                 pending = true; pend_ps = ps; pend_zsq = zsq; pend_i = i;
@@ -683,6 +721,16 @@ void stream_build(int N, bool lower, const double* A, const double* c, const dou
 }
 
 // one CTA per SM; an even count (CTA pairs share the transform stream) unless there is a single tile
+#if MCR_STREAM_TRACE
+extern "C" int mcr_stream_trace_dump(unsigned long long* out /* TRACE_ROLES * TRACE_CAP */, unsigned int* counts /* TRACE_ROLES */, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_stream_trace, sizeof(unsigned long long) * TRACE_ROLES * TRACE_CAP);
+    cudaMemcpyFromSymbol(counts, g_stream_trace_n, sizeof(unsigned int) * TRACE_ROLES);
+    if (reset) { unsigned int z[TRACE_ROLES] = {}; cudaMemcpyToSymbol(g_stream_trace_n, z, sizeof(z)); }
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+#endif
+
 int stream_grid(uint64_t M, int num_sms) {
     const uint64_t tiles = (M + tc::TILE_M - 1) / tc::TILE_M;
     int g = (int)std::min<uint64_t>((uint64_t)num_sms, tiles ? tiles : 1);
