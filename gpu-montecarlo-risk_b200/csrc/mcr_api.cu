@@ -659,11 +659,13 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
             stl.port_x = opt->portfolio_loss_threshold;
             stl.port_acc = e->d_port_acc; stl.port_hist = e->d_port_hist; stl.port_hist_sum = e->d_port_hist_sum;
         }
-        const uint64_t image_key = e->gen * 4 + (uint64_t)port + (dZ ? 2 : 0);   // (the piece order differs between generated and supplied normals)
+        const bool pair = stream_pair(dZ != nullptr, port != 0);
+        stl.pair = pair ? 1 : 0;
+        const uint64_t image_key = e->gen * 8 + (uint64_t)port + (dZ ? 2 : 0) + (pair ? 4 : 0);   // (the piece order differs between generated and supplied normals)
         if (e->stream_gen != image_key || e->stream_x != x || port) {   // (the weights may have changed: a portfolio image is rebuilt)
             e->stream_host_image.resize(bytes);
             e->stream_row_scale.assign(N + port, 1.0);
-            stream_build(N, e->lower, e->A.data(), c.data(), port ? port_row.data() : nullptr, dZ != nullptr, e->stream_host_image.data(), e->stream_row_scale.data());
+            stream_build(N, e->lower, e->A.data(), c.data(), port ? port_row.data() : nullptr, dZ != nullptr, pair, e->stream_host_image.data(), e->stream_row_scale.data());
             MCR_CUDA(cudaStreamSynchronize(s));   // a previous run may still read the old image
             MCR_CUDA(cudaMemcpyAsync(e->d_stream_image, e->stream_host_image.data(), bytes, cudaMemcpyHostToDevice, s));
             e->stream_gen = image_key; e->stream_x = x;
@@ -770,7 +772,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
                 MCR_CUDA(launch_exact(xp, e->num_sms, s));
                 ++launches;
             }
-            fin.block_partials = e->d_block_partials; fin.n_blocks = stream_grid(m, sms);
+            fin.block_partials = e->d_block_partials; fin.n_blocks = stream_grid(m, sms, stl.pair != 0);
             fin.flag_count = e->d_flag_count; fin.flag_cap = FLAG_CAP;
         } else if (plan.wide) {
             wl.M = m; wl.path_offset = path_offset + done; wl.S_out = xp.S_out;

@@ -206,6 +206,7 @@ struct StreamLaunch {
     uint32_t key0, key1;
     int32_t N, k, lower;
     const void* d_image;         // stream_build image on the device
+    int32_t pair;                // CTA-pair form (the image was built for it)
     const double* d_Z;           // supplied normals (M x N fp64, chunk-relative) or nullptr: Philox
     double delta_rel[STREAM_MAX_PASSES], delta_abs[STREAM_MAX_PASSES];   // guard band per pass (relative to ||z||_2), accumulator units
     int32_t* S_out;
@@ -231,8 +232,10 @@ double stream_mma_flops(int N, int port, bool lower);          // fp16 MMA flops
 int stream_normals_per_trial(int N, int port, bool lower);     // normals generated per trial (passes re-derive the leading columns)
 // port_row: nullptr, or N + 1 values (w^T A, then w.mu).  supplied_order: the image for supplied-normals runs (no Z cache: every pass
 // visits its K-blocks in ascending order; generated runs take the cached K-blocks last).  row_scale: out, N (+ 1) entries
-void stream_build(int N, bool lower, const double* A, const double* c, const double* port_row, bool supplied_order, uint8_t* image, double* row_scale);
-int stream_grid(uint64_t M, int num_sms);
+// pair: the image of the CTA-pair form (two rank images, each CTA's half of every piece)
+void stream_build(int N, bool lower, const double* A, const double* c, const double* port_row, bool supplied_order, bool pair, uint8_t* image, double* row_scale);
+bool stream_pair(bool supplied, bool portfolio);   // whether runs of this kind use the CTA-pair form
+int stream_grid(uint64_t M, int num_sms, bool pair);
 cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s);
 
 cudaError_t launch_hist(uint64_t M, const int32_t* S, int nbins, unsigned long long* hist, int num_sms, cudaStream_t s);

@@ -78,6 +78,7 @@ constexpr int ST_ACC_COL = ST_ZSLOTS * ST_ZCOLS;     // first accumulator column
 constexpr int ST_CHUNK_MAX = 256;                    // rows of one transform piece = the N of the MMAs that read it
 constexpr uint32_t ST_PIECE_MAX = ST_CHUNK_MAX * 128;   // 32 KB: up to 256 rows x 64 fp16
 constexpr int ST_RING_MAX = 6;                       // transform pieces in flight (6 x 32 KB; 3 when the Z cache takes its share)
+constexpr int ST_RING_SLOTS = 2 * ST_RING_MAX;       // CTA-pair form: each CTA holds half of every piece, twice as many 16 KB slots
 #ifndef MCR_STREAM_KCACHE_MAX
 #define MCR_STREAM_KCACHE_MAX 3
 #endif
@@ -104,6 +105,7 @@ struct StreamParams {
     StreamPass pass[STREAM_MAX_PASSES];
     float delta_rel[STREAM_MAX_PASSES], delta_abs[STREAM_MAX_PASSES], thr_max[STREAM_MAX_PASSES];   // accumulator units
     const uint8_t* image;      // pieces in consumption order (stream_build)
+    size_t image_rank_bytes;   // CTA-pair form: the image is [halves of CTA 0][halves of CTA 1], this many bytes each
     const double* Z;           // SUPPLIED: M x N fp64 row-major (chunk-relative), else nullptr
     int32_t* S_out;
     uint32_t* flag_list;
@@ -130,6 +132,18 @@ __host__ __device__ inline int stream_acol0(int r0, int kb, int lower) {
     const int a = lower ? 64 * kb - r0 : 0;
     return a > 0 ? a : 0;
 }
+// Two build options that were measured and are OFF (profiles/r02_stream_kernel_development.log, "stream8"):
+//  * MCR_STREAM_DEFER=1: the tcgen05.st of a step are not waited for on the spot; the wait and the hand-over of the Z slot are retired
+//    in the middle of the next step's generation (after its Philox rounds).  Hides the store latency, but the MMAs of every step
+//    start later and the volatile wait splits the generator's instruction schedule: 2 % slower at N = 600, 10 % at N = 256.
+//  * MCR_STREAM_PREFETCH=1: the last pass generates its first uncached K-block right after K-block 0 has been fed (into the cache slot
+//    of K-block 0, which is dead by then), while the tensor core works through the cached K-blocks.  Neutral (+-0.5 %).
+#ifndef MCR_STREAM_DEFER
+#define MCR_STREAM_DEFER 0
+#endif
+#ifndef MCR_STREAM_PREFETCH
+#define MCR_STREAM_PREFETCH 0
+#endif
 // Order in which a pass visits its K-blocks: ascending by default.  MCR_STREAM_CACHED_LAST=1 (build option) makes a later pass take
 // the K-blocks it has to generate first (kcache, kcache + 1, ...) and the cached ones (0 .. kcache - 1) last - feeding a cached block
 // costs the generators nothing while its MMAs are the widest of the pass, so at the end of the pass the generators could already
@@ -187,6 +201,56 @@ __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatil
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// ---- CTA-pair form (tcgen05 cta_group::2; layout and hand-shake checked by tools/pair_layout_check.cu) ----
+// one MMA over both CTAs of the pair: M = 256 (each CTA's 128 A rows from its own TMEM), B = [rows of CTA 0 ; rows of CTA 1] from
+// the same shared-memory offset in both, the accumulator at the same TMEM columns in both; issued by the leader (rank 0) alone
+__device__ __forceinline__ void umma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrive (release, cluster scope) on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+// wait on a barrier that threads of the other CTA arrive on (acquire at cluster scope)
+// (backs off between failed polls: the MMA warp shares its scheduler with four generator warps)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "WAIT_LOOP:\n"
+        "nanosleep.u32 %2;\n"
+        "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20u) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_pair(int n) {   // as make_idesc, M = 256
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
 }  // namespace tc
 
 // 16 normals -> 8 + 8 packed fp16 pairs (hi, lo); same split as store_chunk: hi = rn16(z), lo = rn16(z - hi)
@@ -201,16 +265,24 @@ __device__ __forceinline__ void split16(const float (&z)[16], uint32_t (&hv)[8],
 }
 
 // PORT: the image carries the portfolio row (a separate instantiation: the plain kernel pays nothing for the extension)
-template <bool SUPPLIED, bool PORT>
+// PAIR: the two CTAs of a cluster work as one tensor-core pair (cta_group::2).  Each CTA still generates and reads out its own
+// tile of 128 trials, but it fetches only HALF of every transform piece (rows [r n / 2, (r + 1) n / 2) of the chunk in CTA r) and
+// the leader's MMA warp issues one M = 256 MMA for both tiles: per SM, half the bytes taken in from L2 and half the shared-memory
+// operand reads.  The hand-overs that are named barriers in the single-CTA form (Z slot written, accumulators read out) become
+// cluster-scope mbarriers on the leader; the MMA warp of CTA 1 only relays "my half of the piece has arrived" to the leader.
+template <bool SUPPLIED, bool PORT, bool PAIR>
 __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* s_ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // [ring][ST_PIECE_MAX]
+    uint8_t* s_ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // [ring][PIECE]
     const int RING = p.ring;
-    uint4* s_zcache = reinterpret_cast<uint4*>(s_ring + (size_t)RING * ST_PIECE_MAX);   // [kcache][part][4][128 rows] x 16 B
+    constexpr uint32_t PIECE = PAIR ? ST_PIECE_MAX / 2 : ST_PIECE_MAX;   // bytes of a ring slot
+    uint4* s_zcache = reinterpret_cast<uint4*>(s_ring + (size_t)RING * PIECE);   // [kcache][part][4][128 rows] x 16 B
     // portfolio histogram of this CTA (only with p.portfolio): count << 44 | quantised position sum per bin (port_hist_word)
-    unsigned long long* s_hist = reinterpret_cast<unsigned long long*>(s_ring + (size_t)RING * ST_PIECE_MAX + (size_t)p.kcache * ST_ZCACHE_BYTES);
-    __shared__ uint64_t s_zempty[ST_ZSLOTS], s_bfull[ST_RING_MAX], s_bempty[ST_RING_MAX], s_done;
+    unsigned long long* s_hist = reinterpret_cast<unsigned long long*>(s_ring + (size_t)RING * PIECE + (size_t)p.kcache * ST_ZCACHE_BYTES);
+    __shared__ uint64_t s_zempty[ST_ZSLOTS], s_bfull[ST_RING_SLOTS], s_bempty[ST_RING_SLOTS], s_done;
+    // PAIR, used in the leader only: Z slot written / accumulators read out by the generators of both CTAs; CTA 1's half piece arrived
+    __shared__ uint64_t s_zfull[ST_ZSLOTS], s_accfree, s_bpeer[ST_RING_SLOTS];
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_part_S[ST_PARTS][128], s_part_k1[ST_PARTS][128], s_part_k2[ST_PARTS][128];
     __shared__ float s_part_zsq[ST_PARTS][128];
@@ -225,16 +297,25 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
     const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
     if (tid == 0) {
         for (int b = 0; b < ST_ZSLOTS; ++b) mbar_init(&s_zempty[b], 1);
-        for (int b = 0; b < ST_RING_MAX; ++b) { mbar_init(&s_bfull[b], 1); mbar_init(&s_bempty[b], csz); }
+        // (PAIR: the leader's one commit arrives once on each CTA's copy; otherwise every CTA of the cluster commits to all copies)
+        for (int b = 0; b < ST_RING_SLOTS; ++b) { mbar_init(&s_bfull[b], 1); mbar_init(&s_bempty[b], PAIR ? 1u : csz); mbar_init(&s_bpeer[b], 1); }
         mbar_init(&s_done, 1);
+        for (int b = 0; b < ST_ZSLOTS; ++b) mbar_init(&s_zfull[b], 2 * ST_GEN_THREADS / 32);   // one arrival per generator warp of the pair
+        mbar_init(&s_accfree, 2 * ST_GEN_THREADS / 32);
     }
     if (PORT)
         for (int t = tid; t < MCR_PORTFOLIO_BINS; t += ST_THREADS) s_hist[t] = 0ull;
-    if (warp == ST_MMA_WARP) tmem_alloc(&s_tmem, 512);
+    if (!PAIR && warp == ST_MMA_WARP) tmem_alloc(&s_tmem, 512);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if (csz > 1) cluster_sync_all();   // the partner's barriers exist before anything is multicast to them
+    if (PAIR) {                        // both CTAs allocate the same columns, together
+        if (warp == ST_MMA_WARP) tmem_alloc_pair(&s_tmem, 512);
+        tc_fence_before();
+        __syncthreads();
+        cluster_sync_all();
+    }
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
 
@@ -248,18 +329,42 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
     if (warp == ST_MMA_WARP) {
         // ---- MMA issue: per pass the constant slot, then the K-blocks in order.  A K-block arrives as one hi and one lo piece per
         // chunk of <= 256 rows; a hi piece is multiplied by Zhi and Zlo, a lo piece by Zhi, and each is released right after ----
-        uint32_t zu = 0, rs = 0, rphase = 0;
+        uint32_t zu = 0, rs = 0, rphase = 0, passes = 0;
         auto next_piece = [&]() { if (++rs == (uint32_t)RING) { rs = 0; rphase ^= 1u; } };
+        if (PAIR && crank != 0) {
+            // CTA 1 of a pair: tell the leader when this CTA's half of each piece has landed
+            for (uint64_t n = 0; n < my_tiles; ++n)
+                for (int ps = 0; ps < NPASS; ++ps) {
+                    const int r0 = p.pass[ps].r0, W = p.pass[ps].W, KBN = p.pass[ps].kbn;
+                    for (int st = -1; st < KBN; ++st) {
+                        const int kb = st < 0 ? -1 : stream_kb(ps, st, KBN, p.kcache);
+                        const int w = W - (kb < 0 ? 0 : stream_acol0(r0, kb, LOWER));
+                        const int npieces = (kb < 0 ? 1 : 2) * (w > ST_CHUNK_MAX ? 2 : 1);
+                        for (int q = 0; q < npieces; ++q) {
+                            mbar_wait<20>(&s_bfull[rs], rphase);
+                            if (lane == 0) mbar_arrive_remote(&s_bpeer[rs], 0);
+                            __syncwarp();
+                            next_piece();
+                        }
+                    }
+                }
+        } else
         for (uint64_t n = 0; n < my_tiles; ++n) {
-            for (int ps = 0; ps < NPASS; ++ps) {
+            for (int ps = 0; ps < NPASS; ++ps, ++passes) {
                 const int r0 = p.pass[ps].r0, W = p.pass[ps].W, KBN = p.pass[ps].kbn;
                 for (int st = -1; st < KBN; ++st, ++zu) {
                     const int kb = st < 0 ? -1 : stream_kb(ps, st, KBN, p.kcache);
                     const uint32_t slot = zu & 1u;
                     ST_TRACE(2, 1, kb);                                    // waiting for the Z slot
-                    named_bar_sync(ST_BAR_SLOT + slot, ST_ALL);            // the Z slot is written (tcgen05.st waited for, fenced)
+                    // the Z slot is written (tcgen05.st waited for, fenced) - in both CTAs of a pair
+                    if (PAIR) mbar_wait_cluster(&s_zfull[slot], (zu >> 1) & 1u);
+                    else named_bar_sync(ST_BAR_SLOT + slot, ST_ALL);
                     ST_TRACE(2, 2, kb);
-                    if (kb < 0) { named_bar_sync(ST_BAR_ACC, ST_ALL); ST_TRACE(2, 3, kb); }   // the previous pass has been read out of the accumulators
+                    if (kb < 0) {                                          // the previous pass has been read out of the accumulators
+                        if (PAIR) mbar_wait_cluster(&s_accfree, passes & 1u);
+                        else named_bar_sync(ST_BAR_ACC, ST_ALL);
+                        ST_TRACE(2, 3, kb);
+                    }
                     const int acol0 = kb < 0 ? 0 : stream_acol0(r0, kb, LOWER);
                     const int w = W - acol0, n1 = stream_n1(w), n2 = w - n1;
                     const uint32_t a_hi = tmem_base + slot * ST_ZCOLS, a_lo = a_hi + 32u;
@@ -267,31 +372,44 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                     for (int half = 0; half < (kb < 0 ? 1 : 2); ++half) {
                         for (int c = 0; c < (n2 > 0 ? 2 : 1); ++c) {
                             const uint32_t d = c ? d1 + (uint32_t)n1 : d1;
-                            const uint32_t id = make_idesc(c ? n2 : n1);
+                            const uint32_t id = PAIR ? make_idesc_pair(c ? n2 : n1) : make_idesc(c ? n2 : n1);
                             const bool last = half == (kb < 0 ? 0 : 1) && c == (n2 > 0 ? 1 : 0);
                             mbar_wait<20>(&s_bfull[rs], rphase);
+                            if (PAIR) mbar_wait_cluster(&s_bpeer[rs], rphase);   // ... and CTA 1's half
                             ST_TRACE(2, 4, kb);                            // piece arrived
                             if (elect_one()) {
                                 tc_fence_after();
-                                const uint64_t b = make_desc(smem_u32(s_ring + rs * ST_PIECE_MAX));
+                                const uint64_t b = make_desc(smem_u32(s_ring + rs * PIECE));
+                                auto mma = [&](uint32_t a, uint64_t bd, uint32_t accumulate) {
+                                    if (PAIR) umma_f16_ts_pair(d, a, bd, id, accumulate);
+                                    else umma_f16_ts(d, a, bd, id, accumulate);
+                                };
                                 if (!(MCR_STREAM_ABLATE & 4)) {
                                     if (kb < 0) {   // constants: ones (K columns 0, 1) x [hi | lo] of (mu_i + x) s_i; initialises the accumulators
-                                        umma_f16_ts(d, a_hi, b, id, 0u);
+                                        mma(a_hi, b, 0u);
                                     } else if (half == 0) {   // hi piece: Zhi Bhi, then Zlo Bhi
 #pragma unroll
-                                        for (int ks = 0; ks < KBLOCK / 16; ++ks) umma_f16_ts(d, a_hi + 8 * ks, b + 2 * ks, id, 1u);
+                                        for (int ks = 0; ks < KBLOCK / 16; ++ks) mma(a_hi + 8 * ks, b + 2 * ks, 1u);
 #pragma unroll
-                                        for (int ks = 0; ks < KBLOCK / 16; ++ks) umma_f16_ts(d, a_lo + 8 * ks, b + 2 * ks, id, 1u);
+                                        for (int ks = 0; ks < KBLOCK / 16; ++ks) mma(a_lo + 8 * ks, b + 2 * ks, 1u);
                                     } else {                  // lo piece: Zhi Blo
 #pragma unroll
-                                        for (int ks = 0; ks < KBLOCK / 16; ++ks) umma_f16_ts(d, a_hi + 8 * ks, b + 2 * ks, id, 1u);
+                                        for (int ks = 0; ks < KBLOCK / 16; ++ks) mma(a_hi + 8 * ks, b + 2 * ks, 1u);
                                     }
                                 }
-                                if (csz > 1) umma_commit_multicast(&s_bempty[rs], cmask);   // both rings' slot rs: one more consumer done
-                                else umma_commit(&s_bempty[rs]);
-                                if (last) {
-                                    umma_commit(&s_zempty[slot]);
-                                    if (st == KBN - 1) umma_commit(&s_done);
+                                if (PAIR) {   // every commit of the pair arrives in both CTAs
+                                    umma_commit_pair(&s_bempty[rs]);
+                                    if (last) {
+                                        umma_commit_pair(&s_zempty[slot]);
+                                        if (st == KBN - 1) umma_commit_pair(&s_done);
+                                    }
+                                } else {
+                                    if (csz > 1) umma_commit_multicast(&s_bempty[rs], cmask);   // both rings' slot rs: one more consumer done
+                                    else umma_commit(&s_bempty[rs]);
+                                    if (last) {
+                                        umma_commit(&s_zempty[slot]);
+                                        if (st == KBN - 1) umma_commit(&s_done);
+                                    }
                                 }
                             }
                             __syncwarp();
@@ -307,7 +425,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
         if (lane == 0) {
             uint32_t rs = 0, rphase = 0, piece = 0;
             for (uint64_t n = 0; n < my_tiles; ++n) {
-                const uint8_t* src = p.image;
+                const uint8_t* src = p.image + (PAIR ? (size_t)crank * p.image_rank_bytes : 0);   // PAIR: this CTA's halves
                 for (int ps = 0; ps < NPASS; ++ps) {
                     const int r0 = p.pass[ps].r0, W = p.pass[ps].W, KBN = p.pass[ps].kbn;
                     for (int st = -1; st < KBN; ++st) {
@@ -315,7 +433,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                         const int w = W - (kb < 0 ? 0 : stream_acol0(r0, kb, LOWER)), n1 = stream_n1(w), n2 = w - n1;
                         for (int half = 0; half < (kb < 0 ? 1 : 2); ++half)
                             for (int c = 0; c < (n2 > 0 ? 2 : 1); ++c, ++piece) {
-                                const uint32_t bytes = (uint32_t)(c ? n2 : n1) * 128u;
+                                const uint32_t bytes = (uint32_t)(c ? n2 : n1) * (PAIR ? 64u : 128u);
                                 // slot rs has been consumed by every CTA of the pair (their commits arrive on both copies of s_bempty)
                                 if (piece >= (uint32_t)RING) mbar_wait<20>(&s_bempty[rs], rphase ^ 1u);
                                 ST_TRACE(3, 1, kb);                        // ring slot free, copy issued
@@ -323,8 +441,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_bfull[rs])) : "memory");
                                 } else {
                                     mbar_expect_tx_st(&s_bfull[rs], bytes);   // this CTA's copy, whoever fetches it
-                                    if (csz == 1) bulk_g2s_st(smem_u32(s_ring + rs * ST_PIECE_MAX), src, bytes, &s_bfull[rs]);
-                                    else if ((piece & 1u) == crank) bulk_g2s_multicast(smem_u32(s_ring + rs * ST_PIECE_MAX), src, bytes, &s_bfull[rs], cmask);
+                                    if (PAIR || csz == 1) bulk_g2s_st(smem_u32(s_ring + rs * PIECE), src, bytes, &s_bfull[rs]);
+                                    else if ((piece & 1u) == crank) bulk_g2s_multicast(smem_u32(s_ring + rs * PIECE), src, bytes, &s_bfull[rs], cmask);
                                 }
                                 src += bytes;
                                 if (++rs == (uint32_t)RING) { rs = 0; rphase ^= 1u; }
@@ -352,6 +470,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
         uint32_t p_hits = 0;
         float p_sum = 0.0f, p_sum2 = 0.0f, p_tail = 0.0f;
 
+        // "this warp has read the accumulators of the pass out": to the MMA warp (PAIR: the leader's, from both CTAs)
+        auto acc_free = [&]() {
+            if (PAIR) { __syncwarp(); if (lane == 0) mbar_arrive_remote(&s_accfree, 0); }
+            else named_bar_arrive(ST_BAR_ACC, ST_ALL);
+        };
         // read this thread's groups that end at or below column `upto` (everything left with final_part)
         auto read_columns = [&](int ps, int upto, bool final_part, uint64_t i) {
             const int W = p.pass[ps].W;
@@ -417,7 +540,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
             const uint32_t k1_ = k1, k2_ = k2;
             S_pass = 0u; k1 = 0xFFFFFFFFu; k2 = 0xFFFFFFFFu; c_next = 32 * part;
             tc_fence_before();
-            if (more_work) named_bar_arrive(ST_BAR_ACC, ST_ALL);   // the MMA warp may overwrite the accumulators (next pass)
+            if (more_work) acc_free();   // the MMA warp may overwrite the accumulators (next pass)
             s_part_S[part][row] = S;
             s_part_k1[part][row] = k1_;
             s_part_k2[part][row] = k2_;
@@ -468,7 +591,47 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
             named_bar_sync(ST_BAR_GEN, ST_GEN_THREADS);   // the exchange buffers may be rewritten
         };
 
-        if (my_tiles > 0) named_bar_arrive(ST_BAR_ACC, ST_ALL);   // nothing to read before the very first pass
+        if (my_tiles > 0) acc_free();   // nothing to read before the very first pass
+        // Hand-over of a written Z slot to the MMA warp: wait for the tcgen05.st, fence, arrive.  (MCR_STREAM_DEFER=1 retires it in
+        // the middle of the NEXT step's generation instead, or right away where the next step generates nothing.)
+        bool deferred = false;
+        uint32_t def_slot = 0;
+        auto flush = [&]() {
+            if (deferred) {
+                tmem_store_wait();
+                tc_fence_before();
+                if (PAIR) { __syncwarp(); if (lane == 0) mbar_arrive_remote(&s_zfull[def_slot], 0); }
+                else named_bar_arrive(ST_BAR_SLOT + def_slot, ST_ALL);
+                deferred = false;
+            }
+        };
+        // this thread's 16 normals of K-block kb as fp16 hi / lo pairs; zsq += their squares
+        auto gen16 = [&](int kb, int kend, uint64_t path, const PhiloxPath& rng, uint32_t (&hv)[8], uint32_t (&lv)[8], float& zsq) {
+            const int col0 = KBLOCK * kb + 16 * part;
+            float z[16];
+            if (MCR_STREAM_ABLATE & 2) {
+                flush();
+#pragma unroll
+                for (int q = 0; q < 16; ++q) z[q] = __uint_as_float((((uint32_t)path * 747796405u + (uint32_t)(col0 + q) * 2891336453u) >> 9) | 0x3f000000u);
+            } else if (col0 + 16 <= kend) {
+                rng.normals_multi_between<4>((uint32_t)(col0 >> 2), p.keys, z, [&] { flush(); });
+            } else {   // the K-block that holds the pass's last normal column
+                flush();
+#pragma unroll
+                for (int q = 0; q < 16; ++q) z[q] = 0.0f;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (col0 + 4 * b < kend) rng.normals((uint32_t)((col0 >> 2) + b), p.keys, z + 4 * b);
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    if (col0 + q >= kend) z[q] = 0.0f;
+            }
+            float2 acc2 = make_float2(zsq, 0.0f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc2 = __ffma2_rn(make_float2(z[2 * q], z[2 * q + 1]), make_float2(z[2 * q], z[2 * q + 1]), acc2);
+            zsq = acc2.x + acc2.y;
+            split16(z, hv, lv);
+        };
         bool pending = false;
         int pend_ps = 0;
         float pend_zsq = 0.0f;
@@ -487,6 +650,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
             for (int ps = 0; ps < NPASS; ++ps) {
                 const int KBN = p.pass[ps].kbn, kend = p.pass[ps].kend;
                 float zsq = ps > 0 ? zsq_cached : 0.0f;
+                const bool prefetch = MCR_STREAM_PREFETCH && !MCR_STREAM_CACHED_LAST && !SUPPLIED && ps > 0 && ps == NPASS - 1 && KCACHE > 0 && KBN > KCACHE;
 #pragma unroll 1
                 for (int st = -1; st < KBN; ++st, ++zu) {
                     const int kb = st < 0 ? -1 : stream_kb(ps, st, KBN, KCACHE);
@@ -498,6 +662,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                         const int col0 = KBLOCK * kb + 16 * part;
                         uint4* zck = zc + (size_t)kb * (ST_ZCACHE_BYTES / 16);
                         if (SUPPLIED) {
+                            flush();
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
                                 const double zd = (i < p.M && col0 + q < kend) ? __ldg(zrow + col0 + q) : 0.0;
@@ -510,39 +675,24 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                                 if (q & 1) { hv[q >> 1] |= hb << 16; lv[q >> 1] |= lb << 16; }
                                 else { hv[q >> 1] = hb; lv[q >> 1] = lb; }
                             }
-                        } else if (ps > 0 && kb < KCACHE) {
-                            // generated (and counted into zsq_cached) in the first pass
+                        } else if ((ps > 0 && kb < KCACHE) || (prefetch && kb == KCACHE)) {
+                            // generated (and counted into zsq_cached) in the first pass - or, the first K-block after the cached
+                            // ones in the last pass, at the beginning of this pass into the cache slot of K-block 0 (below)
+                            flush();
+                            if (kb == KCACHE) zck = zc;
                             const uint4 h0 = zck[0], h1 = zck[128], l0 = zck[256], l1 = zck[384];
                             hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w; hv[4] = h1.x; hv[5] = h1.y; hv[6] = h1.z; hv[7] = h1.w;
                             lv[0] = l0.x; lv[1] = l0.y; lv[2] = l0.z; lv[3] = l0.w; lv[4] = l1.x; lv[5] = l1.y; lv[6] = l1.z; lv[7] = l1.w;
                         } else {
-                            float z[16];
-                            if (MCR_STREAM_ABLATE & 2) {
-#pragma unroll
-                                for (int q = 0; q < 16; ++q) z[q] = __uint_as_float((((uint32_t)path * 747796405u + (uint32_t)(col0 + q) * 2891336453u) >> 9) | 0x3f000000u);
-                            } else if (col0 + 16 <= kend) {
-                                rng.normals_multi<4>((uint32_t)(col0 >> 2), p.keys, z);
-                            } else {   // the K-block that holds the pass's last normal column
-#pragma unroll
-                                for (int q = 0; q < 16; ++q) z[q] = 0.0f;
-#pragma unroll
-                                for (int b = 0; b < 4; ++b)
-                                    if (col0 + 4 * b < kend) rng.normals((uint32_t)((col0 >> 2) + b), p.keys, z + 4 * b);
-#pragma unroll
-                                for (int q = 0; q < 16; ++q)
-                                    if (col0 + q >= kend) z[q] = 0.0f;
-                            }
-                            float2 acc2 = make_float2(zsq, 0.0f);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) acc2 = __ffma2_rn(make_float2(z[2 * q], z[2 * q + 1]), make_float2(z[2 * q], z[2 * q + 1]), acc2);
-                            zsq = acc2.x + acc2.y;
-                            split16(z, hv, lv);
+                            gen16(kb, kend, path, rng, hv, lv, zsq);
                             if (ps == 0 && kb < KCACHE) {
                                 zck[0] = make_uint4(hv[0], hv[1], hv[2], hv[3]); zck[128] = make_uint4(hv[4], hv[5], hv[6], hv[7]);
                                 zck[256] = make_uint4(lv[0], lv[1], lv[2], lv[3]); zck[384] = make_uint4(lv[4], lv[5], lv[6], lv[7]);
                                 if (kb == KCACHE - 1) zsq_cached = zsq;
                             }
                         }
+                    } else {
+                        flush();
                     }
                     // stay within ST_ZSLOTS slots of the tensor core
                     if (warp == 0) ST_TRACE(0, 2, kb); else if (warp == 12) ST_TRACE(1, 2, kb);      // normals ready, waiting for the slot
@@ -562,21 +712,32 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                         const uint32_t ones[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // 1.0 in K columns 0 and 1
                         tmem_st8(zaddr, ones);
                     }
-                    tmem_store_wait();
-                    tc_fence_before();
-                    named_bar_arrive(ST_BAR_SLOT + slot, ST_ALL);
-                    if (warp == 0) ST_TRACE(0, 4, kb); else if (warp == 12) ST_TRACE(1, 4, kb);      // handed over
+                    deferred = true; def_slot = slot;
+                    if (!MCR_STREAM_DEFER) flush();
+                    if (warp == 0) ST_TRACE(0, 4, kb); else if (warp == 12) ST_TRACE(1, 4, kb);      // handed over (or stores issued)
                     // the previous pass is read out once this pass's constant slot and first K-block are queued for the tensor core
                     if (st == 0 && pending) {
+                        flush();
                         if (warp == 0) ST_TRACE(0, 5, pend_ps);
                         epilogue(pend_ps, pend_zsq, pend_i, pend_ps == NPASS - 1, true);
                         pending = false;
                         if (warp == 0) ST_TRACE(0, 6, pend_ps);
                     }
+                    // Last pass: its first KCACHE K-blocks come from the cache and cost the generators nothing, while their MMAs are
+                    // the widest of the pass - the generators would wait for Z slots with their next real work (K-block KCACHE)
+                    // still ahead.  That block is generated now, into the cache slot of K-block 0 (read for the last time in this
+                    // step, by this very thread), and taken from there when its turn comes.
+                    if (prefetch && st == 0) {
+                        uint32_t ph[8], pl[8];
+                        gen16(KCACHE, kend, path, rng, ph, pl, zsq);
+                        zc[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]); zc[128] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                        zc[256] = make_uint4(pl[0], pl[1], pl[2], pl[3]); zc[384] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                    }
                 }
                 pending = true; pend_ps = ps; pend_zsq = zsq; pend_i = i;
             }
         }
+        flush();
         if (pending) epilogue(pend_ps, pend_zsq, pend_i, true, false);
         if (PORT) {   // warp sums -> four double atomics per warp (the threads that never saw the portfolio column add zeros)
             float a0 = (float)p_hits, a1 = p_sum, a2 = p_sum2, a3 = p_tail;
@@ -608,7 +769,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
         p.block_partials[2 * (uint64_t)blockIdx.x] = my_tiles ? c : 0;
         p.block_partials[2 * (uint64_t)blockIdx.x + 1] = my_tiles ? s : 0;
     }
-    if (warp == ST_MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == ST_MMA_WARP) {
+        tc_fence_after();
+        if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
@@ -664,17 +829,35 @@ int stream_normals_per_trial(int N, int port, bool lower) {
     return s;
 }
 
-static void put_half(uint8_t* piece, int r, int kk, __half v) { memcpy(piece + tc::operand_offset(0, r, kk), &v, 2); }
+// CTA-pair form (cta_group::2 MMAs, see the kernel): off unless MCR_STREAM_PAIR=1; generated normals without the portfolio row only
+bool stream_pair(bool supplied, bool portfolio) {
+    static const int want = [] { const char* v = getenv("MCR_STREAM_PAIR"); return v && *v ? atoi(v) : 0; }();
+    return want != 0 && !supplied && !portfolio;
+}
+
+// element (row r of n, K column kk) of the piece at byte offset `off` of the image.  pair: the image is two rank images of
+// total / 2 bytes; rank q holds rows [q n / 2, (q + 1) n / 2) of every piece, at half the piece's offset
+static void put_half(uint8_t* image, size_t total, bool pair, size_t off, int n, int r, int kk, __half v) {
+    uint8_t* dst;
+    if (pair) {
+        const int nh = n / 2, q = r / nh;
+        dst = image + (size_t)q * (total / 2) + off / 2 + tc::operand_offset(0, r - q * nh, kk);
+    } else {
+        dst = image + off + tc::operand_offset(0, r, kk);
+    }
+    memcpy(dst, &v, 2);
+}
 
 // image: per pass the constant pieces, then per K-block the hi pieces and the lo pieces, one piece per chunk of <= 256 active rows
 // (stream_n1), each (rows) x 64 fp16 in the K-major 128-byte-swizzled operand layout; row i carries s_i A_ij (row_scale:
 // tc_row_scale), the constant piece s_i (mu_i + x) as hi (K column 0) and lo (K column 1); padded rows hold zeros and a large
 // positive constant
-void stream_build(int N, bool lower, const double* A, const double* c, const double* port_row, bool supplied_order, uint8_t* image, double* row_scale) {
+void stream_build(int N, bool lower, const double* A, const double* c, const double* port_row, bool supplied_order, bool pair, uint8_t* image, double* row_scale) {
     StreamPass ps[STREAM_MAX_PASSES];
     const int port = port_row ? 1 : 0;
     const int np = stream_plan(N, port, lower, ps);
-    memset(image, 0, stream_image_bytes(N, port, lower));
+    const size_t total = stream_image_bytes(N, port, lower);
+    memset(image, 0, total);
     // row i < N: transform row i and the constant mu_i + x; row N (portfolio): w^T A and the constant w.mu
     auto entry = [&](int i, int j) { return i < N ? A[(size_t)i * N + j] : port_row[j]; };
     auto constant = [&](int i) { return i < N ? c[i] : port_row[N]; };
@@ -688,7 +871,7 @@ void stream_build(int N, bool lower, const double* A, const double* c, const dou
         hi = __float2half_rn((float)v);
         lo = __float2half_rn((float)(v - (double)__half2float(hi)));
     };
-    uint8_t* out = image;
+    size_t out = 0;
     for (int q = 0; q < np; ++q) {
         const int r0 = ps[q].r0, W = ps[q].W;
         const int kcache = np > 1 ? std::min(ST_KCACHE_MAX, ps[0].kend / tc::KBLOCK) : 0;   // as stream_launch sets it (generated normals)
@@ -696,14 +879,14 @@ void stream_build(int N, bool lower, const double* A, const double* c, const dou
             const int kb = st < 0 ? -1 : stream_kb(q, st, ps[q].kbn, supplied_order ? 0 : kcache);
             const int a0 = kb < 0 ? 0 : stream_acol0(r0, kb, lower), w = W - a0, n1 = stream_n1(w);
             // piece of (half, chunk): halves outer, chunks inner, as the kernel consumes them
-            uint8_t* piece[2][2] = {{out, out + (size_t)n1 * 128}, {out + (size_t)w * 128, out + (size_t)(w + n1) * 128}};
+            const size_t piece[2][2] = {{out, out + (size_t)n1 * 128}, {out + (size_t)w * 128, out + (size_t)(w + n1) * 128}};
             for (int r = 0; r < w; ++r) {
-                const int i = r0 + a0 + r, ch = r >= n1 ? 1 : 0, rl = r - (ch ? n1 : 0);
+                const int i = r0 + a0 + r, ch = r >= n1 ? 1 : 0, rl = r - (ch ? n1 : 0), nch = ch ? w - n1 : n1;
                 __half hi, lo;
                 if (kb < 0) {
                     split(i < rows ? constant(i) * row_scale[i] : TC_PAD_ROW, hi, lo);
-                    put_half(piece[0][ch], rl, 0, hi);
-                    put_half(piece[0][ch], rl, 1, lo);
+                    put_half(image, total, pair, piece[0][ch], nch, rl, 0, hi);
+                    put_half(image, total, pair, piece[0][ch], nch, rl, 1, lo);
                     continue;
                 }
                 if (i >= rows) break;
@@ -711,8 +894,8 @@ void stream_build(int N, bool lower, const double* A, const double* c, const dou
                     const int j = tc::KBLOCK * kb + kk;
                     if (j >= ps[q].kend) break;
                     split(entry(i, j) * row_scale[i], hi, lo);
-                    put_half(piece[0][ch], rl, kk, hi);
-                    put_half(piece[1][ch], rl, kk, lo);
+                    put_half(image, total, pair, piece[0][ch], nch, rl, kk, hi);
+                    put_half(image, total, pair, piece[1][ch], nch, rl, kk, lo);
                 }
             }
             out += (size_t)w * 128 * (kb < 0 ? 1 : 2);
@@ -731,10 +914,11 @@ extern "C" int mcr_stream_trace_dump(unsigned long long* out /* TRACE_ROLES * TR
 }
 #endif
 
-int stream_grid(uint64_t M, int num_sms) {
+int stream_grid(uint64_t M, int num_sms, bool pair) {
     const uint64_t tiles = (M + tc::TILE_M - 1) / tc::TILE_M;
     int g = (int)std::min<uint64_t>((uint64_t)num_sms, tiles ? tiles : 1);
     if (g > 1) g &= ~1;
+    if (pair && g < 2) g = 2;   // a CTA pair always; the second CTA of a single-tile run works on a ghost tile
     return g;
 }
 
@@ -756,8 +940,9 @@ cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
     // K-blocks of normals that lie entirely inside the first pass are kept in shared memory for the later passes; the ring of
     // transform pieces gets the rest of 6 x 32 KB
     p.kcache = (p.npass > 1 && !l.d_Z) ? std::min(ST_KCACHE_MAX, p.pass[0].kend / tc::KBLOCK) : 0;
-    p.ring = ST_RING_MAX - p.kcache;
-    const size_t smem = (size_t)p.ring * ST_PIECE_MAX + (size_t)p.kcache * ST_ZCACHE_BYTES + 1024 + (l.portfolio ? (size_t)MCR_PORTFOLIO_BINS * 8 : 0);
+    p.ring = (ST_RING_MAX - p.kcache) * (l.pair ? 2 : 1);   // (pair: slots of half the size)
+    p.image_rank_bytes = stream_image_bytes(l.N, l.portfolio ? 1 : 0, l.lower != 0) / 2;
+    const size_t smem = (size_t)(ST_RING_MAX - p.kcache) * ST_PIECE_MAX + (size_t)p.kcache * ST_ZCACHE_BYTES + 1024 + (l.portfolio ? (size_t)MCR_PORTFOLIO_BINS * 8 : 0);
     p.portfolio = l.portfolio;
     if (l.portfolio) {
         p.port_col = l.N - p.pass[p.npass - 1].r0;
@@ -766,27 +951,32 @@ cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
         p.port_acc = l.port_acc; p.port_hist = l.port_hist; p.port_hist_sum = l.port_hist_sum;
     }
     p.keys.set(l.key0, l.key1);
-    const int grid = stream_grid(l.M, num_sms);
+    const int grid = stream_grid(l.M, num_sms, l.pair != 0);
+    if (l.pair && (l.d_Z || l.portfolio)) return cudaErrorInvalidValue;
     static const int want_cluster = [] { const char* v = getenv("MCR_STREAM_CLUSTER"); return v && *v ? atoi(v) : 2; }();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(ST_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (want_cluster == 2 && grid % 2 == 0) ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = (l.pair || (want_cluster == 2 && grid % 2 == 0)) ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e;
     if (l.d_Z) {
-        e = cudaFuncSetAttribute(tc_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(tc_stream_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<true, false>, p);
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<true, false, false>, p);
     } else if (l.portfolio) {
-        e = cudaFuncSetAttribute(tc_stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(tc_stream_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, true>, p);
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, true, false>, p);
+    } else if (l.pair) {
+        e = cudaFuncSetAttribute(tc_stream_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, false, true>, p);
     } else {
-        e = cudaFuncSetAttribute(tc_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(tc_stream_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, false>, p);
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, false, false>, p);
     }
     return e != cudaSuccess ? e : cudaGetLastError();
 }
