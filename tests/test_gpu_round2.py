@@ -331,3 +331,49 @@ def test_plugin_device_cholesky_option(monkeypatch):
     b = oracle_lib.run_model_struct(plugin.get_cuda_model, m.mu, m.Sigma, m.k, m.x, 300_000, 67)
     assert a["rc"] == 0 and b["rc"] == 0 and a["count"] == b["count"]
     np.testing.assert_array_equal(a["S_values"], b["S_values"])
+
+
+_PAIR_CHILD = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+import oracle_lib
+from mcr_b200 import api
+from mcr_b200.synthetic import synthetic_model
+oracle = oracle_lib.Oracle()
+e = api.Engine(0)
+out = []
+for N, mode, M in [(144, api.TRANSFORM_GSL_FULL, 5_000), (385, api.TRANSFORM_LOWER, 6_000), (600, api.TRANSFORM_LOWER, 148 * 128 + 77),
+                   (600, api.TRANSFORM_LOWER, 100), (1000, api.TRANSFORM_LOWER, 2_500)]:
+    m = synthetic_model(N)
+    A = e.upload_sigma(m.mu, m.Sigma, mode)
+    Z, _ = e.dump_normals(M, 19)
+    ro = oracle.run_normals(A, m.mu, m.k, m.x, Z)
+    h = api.simulate_host(m.mu, A, M, 19, m.x, m.k, a_is_lower=(mode == api.TRANSFORM_LOWER), want_S_values=True)
+    out.append({"N": N, "kernel": h.kernel, "same_S": bool(np.array_equal(h.S_values, ro["S_values"])),
+                "same_counts": (h.count, h.sum_S) == (ro["count"], ro["sum_S"]), "rechecked": h.n_rechecked, "M": M})
+m = synthetic_model(600)
+e.upload_sigma(m.mu, m.Sigma)
+fast = e.run(3_000_000, 67, m.x, m.k)
+exact = e.run(3_000_000, 67, m.x, m.k, kernel=api.KERNEL_EXACT)
+out.append({"N": 600, "kernel": fast.kernel, "same_S": True, "same_counts": (fast.count, fast.sum_S) == (exact.count, exact.sum_S),
+            "rechecked": fast.n_rechecked, "M": 3_000_000})
+print(json.dumps(out))
+"""
+
+
+def test_cta_pair_form_of_the_streamed_kernel_is_bit_identical():
+    """MCR_STREAM_PAIR=1 (tcgen05 cta_group::2: one M = 256 MMA per CTA pair, half of every transform piece per CTA; read once per
+    process, hence the child): one, two and three passes, dense and lower-triangular, a run of a single tile (the second CTA of
+    the pair works on a ghost tile), per-trial S against the fp64 oracle and AUTO == EXACT over 3e6 trials at N = 600."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, MCR_STREAM_PAIR="1")
+    p = subprocess.run([sys.executable, "-c", _PAIR_CHILD, str(PKG), str(ROOT / "tests")], env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    res = json.loads(p.stdout.strip().splitlines()[-1])
+    assert len(res) == 6
+    for r in res:
+        assert r["kernel"] == "tensor" and r["same_S"] and r["same_counts"], r
+        assert r["rechecked"] < max(r["M"] // 5, 50), r
