@@ -609,6 +609,9 @@ def main():
             "sm_reserve": sm_reserve,
             "e2e": e2e, "gpu_launches": launches_per_step * steps,
             "roofline": roof, "cpu_baseline": cpu, "gpu_baseline": gpu_ref, "supplied_normals": supplied, "configs": configs,
+            # SURVEY.md section 8(d) secondary lines: normals consumed per second (N per trial) and the dense-equivalent flop rate
+            "secondary": {"normals_per_s": value * N, "dense_equivalent_tflops": value * (2 * N * N + 2 * N) / 1e12,
+                          "note": "whole job, over the step time; N normals and 2N^2+2N flops per simulation"},
             "result": {"count": res.count, "sum_S": res.sum_S, "P_hat": res.P_hat, "n_rechecked": res.n_rechecked},
         }
         print(json.dumps(line))
