@@ -26,12 +26,18 @@
 //     |accumulator| keys of the row decide between "no decision near the threshold", "exactly one" (that row alone goes to
 //     exact_pairs_kernel) and "several" (the whole trial goes to the fp64 kernel), exactly like the row-slab kernel.
 //   * SUPPLIED = true: the normals come from the caller (M x N fp64 in HBM, serial.c:67-69 layout) instead of Philox:
-//     parity mode 1 "fed identical pre-generated normals through the interface" reaches the tensor path.
+//     parity mode 1 "fed identical pre-generated normals through the interface" reaches the tensor path.  The matrix is read
+//     through a 2-D TMA tensor map, one box of 16 columns x 128 trials (16 KB, 128-byte swizzle) per generator part and
+//     K-block, by a loader warp of its own into two box slots per part (cp.async.bulk.tensor + full / empty mbarriers): a thread
+//     reading its own row element by element makes every warp load touch 32 lines (measured 0.55 - 0.7 TB/s at N = 600, against
+//     1.6 TB/s through the boxes).  Rows past M and columns past N are zero-filled by the TMA unit.  (Odd N or an unaligned
+//     matrix: rows are not 16-byte aligned, the element loads stay.)
 #include "../../include/mcr_b200.h"
 #include "mcr_internal.h"
 #include "mcr_rng.cuh"
 #include "mcr_tc_common.cuh"
 
+#include <cuda.h>   // CUtensorMap (the encode function is fetched through cudaGetDriverEntryPoint: no libcuda link)
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -77,7 +83,10 @@ constexpr int ST_ZCOLS = 64;                         // TMEM columns of a Z slot
 constexpr int ST_ACC_COL = ST_ZSLOTS * ST_ZCOLS;     // first accumulator column
 constexpr int ST_CHUNK_MAX = 256;                    // rows of one transform piece = the N of the MMAs that read it
 constexpr uint32_t ST_PIECE_MAX = ST_CHUNK_MAX * 128;   // 32 KB: up to 256 rows x 64 fp16
-constexpr int ST_RING_MAX = 6;                       // transform pieces in flight (6 x 32 KB; 3 when the Z cache takes its share)
+#ifndef MCR_STREAM_RING_MAX
+#define MCR_STREAM_RING_MAX 6
+#endif
+constexpr int ST_RING_MAX = MCR_STREAM_RING_MAX;     // transform pieces in flight (6 x 32 KB; 3 when the Z cache takes its share)
 constexpr int ST_RING_SLOTS = 2 * ST_RING_MAX;       // CTA-pair form: each CTA holds half of every piece, twice as many 16 KB slots
 #ifndef MCR_STREAM_KCACHE_MAX
 #define MCR_STREAM_KCACHE_MAX 3
@@ -86,8 +95,23 @@ constexpr int ST_KCACHE_MAX = MCR_STREAM_KCACHE_MAX;                     // K-bl
 constexpr uint32_t ST_ZCACHE_BYTES = 128 * 64 * 4;   // one K-block of Z: 128 trials x 64 columns x (hi + lo)
 constexpr int ST_PARTS = 4;                          // generator threads per trial: 16 of a K-block's 64 columns each
 constexpr int ST_GEN_THREADS = 128 * ST_PARTS;
-constexpr int ST_THREADS = ST_GEN_THREADS + 64;      // + MMA-issue warp + loader warp
-constexpr int ST_MMA_WARP = ST_GEN_THREADS / 32, ST_LOAD_WARP = ST_MMA_WARP + 1;
+constexpr int ST_THREADS = ST_GEN_THREADS + 64;      // + MMA-issue warp + transform loader warp
+constexpr int ST_THREADS_SUPPLIED = ST_THREADS + 32; // + Z loader warp (the supplied-normals instantiation only)
+constexpr int ST_MMA_WARP = ST_GEN_THREADS / 32, ST_LOAD_WARP = ST_MMA_WARP + 1, ST_ZLOAD_WARP = ST_MMA_WARP + 2;
+// supplied normals: TMA boxes (16 columns x 128 trials of fp64, 16 KB each), ST_ZDEPTH per generator part.  Every box slot belongs to
+// ONE part: its four warps take the slot's uses in order, so a parity wait is never more than one phase ahead (boxes land out of
+// order; with slots shared between parts a fast warp could wait for use u + 1 of a slot whose use u has not landed yet, and a
+// parity wait two phases ahead passes at once).
+#ifndef MCR_STREAM_ZDEPTH
+#define MCR_STREAM_ZDEPTH 2
+#endif
+constexpr int ST_ZDEPTH = MCR_STREAM_ZDEPTH;
+constexpr int ST_ZBOX = ST_PARTS * ST_ZDEPTH;
+constexpr uint32_t ST_ZBOX_BYTES = 16 * 128 * 8;
+#ifndef MCR_STREAM_ZRING
+#define MCR_STREAM_ZRING (MCR_STREAM_ZDEPTH >= 2 ? 2 : 4)
+#endif
+constexpr int ST_ZRING = MCR_STREAM_ZRING;           // ... next to which the transform ring keeps two (four) 32 KB pieces
 constexpr int ST_ALL = ST_GEN_THREADS + 32;          // generators + MMA warp
 constexpr int ST_BAR_SLOT = 1, ST_BAR_ACC = 3, ST_BAR_GEN = 4;   // named barriers: 1, 2 = Z slot full; accumulators free; generators only
 constexpr uint32_t ST_KEY_MASK = 0xFFFFFC00u;        // epilogue keys: bits 10.. = |accumulator| << 1 (truncated), 1..9 = column, 0 = sign
@@ -107,6 +131,7 @@ struct StreamParams {
     const uint8_t* image;      // pieces in consumption order (stream_build)
     size_t image_rank_bytes;   // CTA-pair form: the image is [halves of CTA 0][halves of CTA 1], this many bytes each
     const double* Z;           // SUPPLIED: M x N fp64 row-major (chunk-relative), else nullptr
+    int32_t ztma;              // SUPPLIED: 1 = Z is read through the tensor map (second kernel parameter), 0 = element loads
     int32_t* S_out;
     uint32_t* flag_list;
     uint32_t* flag_count;
@@ -196,6 +221,12 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask)
                  : "memory");
 }
+// one box of a 2-D tensor map (column c0, row r0) into shared memory, signalled on the mbarrier with its bytes
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int32_t c0, int32_t r0, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+                 "l"(map), "r"(c0), "r"(r0), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -271,7 +302,7 @@ __device__ __forceinline__ void split16(const float (&z)[16], uint32_t (&hv)[8],
 // operand reads.  The hand-overs that are named barriers in the single-CTA form (Z slot written, accumulators read out) become
 // cluster-scope mbarriers on the leader; the MMA warp of CTA 1 only relays "my half of the piece has arrived" to the leader.
 template <bool SUPPLIED, bool PORT, bool PAIR>
-__global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamParams p) {
+__global__ void __launch_bounds__(SUPPLIED ? ST_THREADS_SUPPLIED : ST_THREADS, 1) tc_stream_kernel(const StreamParams p, const __grid_constant__ CUtensorMap zmap) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* s_ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // [ring][PIECE]
@@ -283,6 +314,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
     __shared__ uint64_t s_zempty[ST_ZSLOTS], s_bfull[ST_RING_SLOTS], s_bempty[ST_RING_SLOTS], s_done;
     // PAIR, used in the leader only: Z slot written / accumulators read out by the generators of both CTAs; CTA 1's half piece arrived
     __shared__ uint64_t s_zfull[ST_ZSLOTS], s_accfree, s_bpeer[ST_RING_SLOTS];
+    // SUPPLIED through TMA: the ring of Z boxes behind the transform ring; filled by the Z loader, each read by the four warps of a part
+    __shared__ uint64_t s_zbfull[ST_ZBOX], s_zbempty[ST_ZBOX];
+    uint8_t* const s_zbox = s_ring + (size_t)RING * PIECE;
+    const bool ZTMA = SUPPLIED && p.ztma != 0;
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_part_S[ST_PARTS][128], s_part_k1[ST_PARTS][128], s_part_k2[ST_PARTS][128];
     __shared__ float s_part_zsq[ST_PARTS][128];
@@ -302,6 +337,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
         mbar_init(&s_done, 1);
         for (int b = 0; b < ST_ZSLOTS; ++b) mbar_init(&s_zfull[b], 2 * ST_GEN_THREADS / 32);   // one arrival per generator warp of the pair
         mbar_init(&s_accfree, 2 * ST_GEN_THREADS / 32);
+        for (int b = 0; b < ST_ZBOX; ++b) { mbar_init(&s_zbfull[b], 1); mbar_init(&s_zbempty[b], 4); }
     }
     if (PORT)
         for (int t = tid; t < MCR_PORTFOLIO_BINS; t += ST_THREADS) s_hist[t] = 0ull;
@@ -452,12 +488,31 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
             }
         }
         __syncwarp();
+    } else if (warp == ST_ZLOAD_WARP) {
+        // ---- supplied normals: the Z boxes in the order the generators consume them (tile, pass, K-block, part) ----
+        if (ZTMA && lane == 0) {
+            uint32_t seq = 0;
+            for (uint64_t n = 0; n < my_tiles; ++n) {
+                const uint64_t tile = blockIdx.x + (uint64_t)gridDim.x * n;
+                const int32_t r0 = (int32_t)min(tile * TILE_M, (uint64_t)0x7fffff00u);   // (a ghost tile lies past M: zero-filled)
+                for (int ps = 0; ps < NPASS; ++ps)
+                    for (int kb = 0; kb < p.pass[ps].kbn; ++kb)
+                        for (int part = 0; part < ST_PARTS; ++part, ++seq) {
+                            const uint32_t slot = seq % ST_ZBOX, use = seq / ST_ZBOX;   // (slot % ST_PARTS == part)
+                            if (use > 0) mbar_wait<20>(&s_zbempty[slot], (use - 1u) & 1u);
+                            mbar_expect_tx_st(&s_zbfull[slot], ST_ZBOX_BYTES);
+                            tma_load_2d(smem_u32(s_zbox + (size_t)slot * ST_ZBOX_BYTES), &zmap, KBLOCK * kb + 16 * part, r0, &s_zbfull[slot]);
+                        }
+            }
+        }
+        __syncwarp();
     } else {
         // ---- generator + epilogue warps: warp w owns TMEM lanes 32 (w % 4) .. +31 (trial rows) and columns 16 (w / 4) .. +15 of a K-block ----
         const int quarter = warp & 3, part = warp >> 2, row = 32 * quarter + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * quarter) << 16);
         const int KCACHE = SUPPLIED ? 0 : p.kcache;
         uint32_t zu = 0, done_parity = 0, cnt = 0, sum_s = 0;
+        uint32_t zk = 0;   // (supplied normals through TMA) K-block steps taken so far: box sequence number = 4 zk + part
         // state of the trial in this thread's row across the passes of a tile (kept by the part-0 thread of the row)
         uint32_t S_tot = 0, n_amb = 0, amb = 0;
 
@@ -663,9 +718,31 @@ __global__ void __launch_bounds__(ST_THREADS, 1) tc_stream_kernel(const StreamPa
                         uint4* zck = zc + (size_t)kb * (ST_ZCACHE_BYTES / 16);
                         if (SUPPLIED) {
                             flush();
+                            double zbuf[16];
+                            if (ZTMA) {
+                                // this part's box: row = trial, 128 bytes = 16 doubles, 16-byte chunk c stored at c ^ (row % 8)
+                                const uint32_t seq = 4u * zk + (uint32_t)part, slot = seq % ST_ZBOX;
+                                mbar_wait<20>(&s_zbfull[slot], (seq / ST_ZBOX) & 1u);
+                                const uint8_t* brow = s_zbox + (size_t)slot * ST_ZBOX_BYTES + (size_t)row * 128;
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) {
+                                    const double2 v = *reinterpret_cast<const double2*>(brow + ((c ^ (row & 7)) << 4));
+                                    zbuf[2 * c] = v.x; zbuf[2 * c + 1] = v.y;
+                                }
+                                // The box goes back to the loader, whose refill is an ASYNC-proxy write: a proxy fence orders this
+                                // thread's (generic-proxy) reads of the box before it.  Without the fence the arrive overtakes the
+                                // loads (SASS: eight LDS.128, then SYNCS.ARRIVE at once) and, with the tensor core streaming its
+                                // operand out of shared memory, the refill lands before they are served - measured: up to 4 % wrong
+                                // trials whenever a box lay in the first 128 KB of the dynamic region, none with all boxes above
+                                // (profiles/r02_stream_ztma_experiment.log).
+                                fence_async_smem();
+                                __syncwarp();
+                                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_zbempty[slot])) : "memory");
+                                ++zk;
+                            }
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
-                                const double zd = (i < p.M && col0 + q < kend) ? __ldg(zrow + col0 + q) : 0.0;
+                                const double zd = ZTMA ? (col0 + q < kend ? zbuf[q] : 0.0) : ((i < p.M && col0 + q < kend) ? __ldg(zrow + col0 + q) : 0.0);
                                 const float zf = (float)zd;
                                 zsq = fmaf(zf, zf, zsq);
                                 // split the fp64 normal itself: hi = rn16(z), lo = rn16(z - hi)
@@ -922,6 +999,24 @@ int stream_grid(uint64_t M, int num_sms, bool pair) {
     return g;
 }
 
+// tensor map of the caller's normals: fp64, M rows of N, boxes of 16 columns x 128 rows, 128-byte swizzle, zero fill outside
+static bool encode_z_map(const double* Z, uint64_t M, int N, CUtensorMap* map) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const encode_fn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        return reinterpret_cast<encode_fn>(fn);
+    }();
+    if (!encode || (N & 1) || (reinterpret_cast<uintptr_t>(Z) & 15) || M == 0) return false;   // rows must start 16-byte aligned
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * 8};
+    const cuuint32_t box[2] = {16, 128}, estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(Z), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
     StreamParams p{};
     p.M = l.M; p.path_offset = l.path_offset; p.key0 = l.key0; p.key1 = l.key1;
@@ -942,7 +1037,11 @@ cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
     p.kcache = (p.npass > 1 && !l.d_Z) ? std::min(ST_KCACHE_MAX, p.pass[0].kend / tc::KBLOCK) : 0;
     p.ring = (ST_RING_MAX - p.kcache) * (l.pair ? 2 : 1);   // (pair: slots of half the size)
     p.image_rank_bytes = stream_image_bytes(l.N, l.portfolio ? 1 : 0, l.lower != 0) / 2;
-    const size_t smem = (size_t)(ST_RING_MAX - p.kcache) * ST_PIECE_MAX + (size_t)p.kcache * ST_ZCACHE_BYTES + 1024 + (l.portfolio ? (size_t)MCR_PORTFOLIO_BINS * 8 : 0);
+    alignas(64) CUtensorMap zmap;
+    memset(&zmap, 0, sizeof(zmap));
+    static const bool no_ztma = [] { const char* v = getenv("MCR_STREAM_NO_ZTMA"); return v && *v && atoi(v) != 0; }();   // A/B runs
+    if (l.d_Z && !no_ztma && encode_z_map(l.d_Z, l.M, l.N, &zmap)) { p.ztma = 1; p.ring = ST_ZRING; }
+    const size_t smem = p.ztma ? (size_t)ST_ZRING * ST_PIECE_MAX + (size_t)ST_ZBOX * ST_ZBOX_BYTES + 1024 : (size_t)(ST_RING_MAX - p.kcache) * ST_PIECE_MAX + (size_t)p.kcache * ST_ZCACHE_BYTES + 1024 + (l.portfolio ? (size_t)MCR_PORTFOLIO_BINS * 8 : 0);
     p.portfolio = l.portfolio;
     if (l.portfolio) {
         p.port_col = l.N - p.pass[p.npass - 1].r0;
@@ -955,7 +1054,7 @@ cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
     if (l.pair && (l.d_Z || l.portfolio)) return cudaErrorInvalidValue;
     static const int want_cluster = [] { const char* v = getenv("MCR_STREAM_CLUSTER"); return v && *v ? atoi(v) : 2; }();
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(ST_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(l.d_Z ? ST_THREADS_SUPPLIED : ST_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (l.pair || (want_cluster == 2 && grid % 2 == 0)) ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -964,19 +1063,19 @@ cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
     if (l.d_Z) {
         e = cudaFuncSetAttribute(tc_stream_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<true, false, false>, p);
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<true, false, false>, p, zmap);
     } else if (l.portfolio) {
         e = cudaFuncSetAttribute(tc_stream_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, true, false>, p);
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, true, false>, p, zmap);
     } else if (l.pair) {
         e = cudaFuncSetAttribute(tc_stream_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, false, true>, p);
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, false, true>, p, zmap);
     } else {
         e = cudaFuncSetAttribute(tc_stream_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, false, false>, p);
+        e = cudaLaunchKernelEx(&cfg, tc_stream_kernel<false, false, false>, p, zmap);
     }
     return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -377,3 +377,23 @@ def test_cta_pair_form_of_the_streamed_kernel_is_bit_identical():
     for r in res:
         assert r["kernel"] == "tensor" and r["same_S"] and r["same_counts"], r
         assert r["rechecked"] < max(r["M"] // 5, 50), r
+
+
+@pytest.mark.parametrize("N,mode", [(600, api.TRANSFORM_LOWER), (600, api.TRANSFORM_GSL_FULL), (300, api.TRANSFORM_LOWER), (1000, api.TRANSFORM_LOWER),
+                                    (257, api.TRANSFORM_LOWER)])
+def test_supplied_normals_streamed_repeatedly(engine, N, mode):
+    """The streamed kernel's supplied-normals path reads the caller's matrix through a TMA tensor map into a ring of boxes that
+    generator warps read with ordinary loads (even N; odd N = 257 keeps the element loads).  The hand-back of a box to the loader
+    needs a proxy fence (generic reads before the async-proxy refill): without it a few trials in a thousand came out wrong, in
+    some runs only - so this one repeats a run that keeps the tensor core busy, per-trial S against the fp64 kernel on the same
+    normals, several tiles per CTA."""
+    m = synthetic_model(N)
+    engine.upload_sigma(m.mu, m.Sigma, mode)
+    M = 148 * 128 * 2 + 77
+    Z = np.random.default_rng(N).standard_normal((M, N))
+    exact = engine.run_with_normals(Z, m.x, m.k, kernel=api.KERNEL_EXACT)
+    for _ in range(6):
+        r = engine.run_with_normals(Z, m.x, m.k, kernel=api.KERNEL_TENSOR)
+        assert r.kernel == "tensor"
+        np.testing.assert_array_equal(r.S_values, exact.S_values)
+        assert (r.count, r.sum_S) == (exact.count, exact.sum_S)

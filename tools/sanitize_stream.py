@@ -14,4 +14,14 @@ for N, M in ((600, 700), (50, 2000)):
     x = e.run(M, 67, m.x, m.k, kernel=api.KERNEL_EXACT)
     assert (r.count, r.sum_S) == (x.count, x.sum_S)
     print(N, r.kernel, r.count, "ok")
+# supplied normals through the TMA boxes (N > 128, even N) and through element loads (odd N)
+import numpy as np
+for N, M in ((600, 500), (301, 300)):
+    m = synthetic_model(N)
+    e.upload_sigma(m.mu, m.Sigma)
+    Z = np.random.default_rng(N).standard_normal((M, N))
+    r = e.run_with_normals(Z, m.x, m.k, kernel=api.KERNEL_TENSOR)
+    x = e.run_with_normals(Z, m.x, m.k, kernel=api.KERNEL_EXACT)
+    assert (r.count, r.sum_S) == (x.count, x.sum_S) and (r.S_values == x.S_values).all()
+    print(N, "supplied", r.kernel, r.count, "ok")
 e.close()
