@@ -340,6 +340,16 @@ static int make_plan(const mcr_engine* e, const mcr_run_options* opt, bool norma
         plan->kernel = MCR_KERNEL_TENSOR; plan->NT = tc_padded_n(plan->rows);
         return 0;
     }
+    // Supplied normals, N <= 128.  The streamed kernel reads the caller's matrix through TMA boxes (even N: rows 16-byte aligned) at
+    // 2.0 - 3.0 TB/s for N = 50 ... 128, the tile kernel's supplied-normals instantiation (element loads) at 0.8 - 1.6, the FFMA kernel
+    // at 4.3 (N <= 32), 3.3 (N = 50), 2.1 (N = 64), 1.4 (N = 100), 0.9 (N = 128) (profiles/r02_supplied_normals_bandwidth.log):
+    // on request (TENSOR) even N >= 36 takes the streamed kernel, AUTO takes it from N = 64.  MCR_SUPPLIED_TENSOR=tile keeps the tile kernel.
+    static const bool supplied_tile = [] { const char* v = getenv("MCR_SUPPLIED_TENSOR"); return v && !strcmp(v, "tile"); }();
+    if (normals && !supplied_tile && (e->N & 1) == 0 && stream_supported(e->N, 0) &&
+        ((want == MCR_KERNEL_TENSOR && e->N >= 36) || (want == MCR_KERNEL_AUTO && e->N >= 64))) {
+        plan->kernel = MCR_KERNEL_TENSOR; plan->stream = true; plan->NT = (plan->rows + 15) & ~15;
+        return 0;
+    }
     if (want == MCR_KERNEL_TENSOR) {
         if (!tc_ok) return fail("tensor-core kernel covers N <= %d in this build (N=%d)", tc_max_n(), e->N);
         plan->kernel = MCR_KERNEL_TENSOR; plan->NT = normals ? tc_supplied_padded_n() : tc_padded_n(plan->rows);

@@ -342,9 +342,14 @@ def test_kernel_selection(engine):
     m = synthetic_model(64)
     engine.upload_sigma(m.mu, m.Sigma)
     assert engine.run(1000, 1, m.x, m.k).kernel == "tensor"    # N >= 36: tensor-core kernel
-    # supplied normals: AUTO keeps the FFMA kernel up to N = 128, an explicit request reaches the (streamed) tensor kernel
+    # supplied normals: AUTO keeps the FFMA kernel below N = 64 (and for odd N up to 128), from there the streamed tensor kernel
+    # reads the matrix faster (TMA boxes); an explicit request reaches a tensor kernel at every N
     Z = np.zeros((4, 64))
-    assert engine.run_with_normals(Z, m.x, m.k).kernel == "ffma"
+    assert engine.run_with_normals(Z, m.x, m.k).kernel == "tensor"
+    m50 = synthetic_model(50)
+    engine.upload_sigma(m50.mu, m50.Sigma)
+    assert engine.run_with_normals(np.zeros((4, 50)), m50.x, m50.k).kernel == "ffma"
+    engine.upload_sigma(m.mu, m.Sigma)
     rt = engine.run_with_normals(Z, m.x, m.k, kernel=api.KERNEL_TENSOR)
     assert rt.kernel == "tensor" and rt.count == 0 and list(rt.S_values) == [0, 0, 0, 0]
     with pytest.raises(api.McrError, match="portfolio outputs are not available with supplied normals"):

@@ -262,11 +262,12 @@ def test_reference_cuda_model_agrees_within_3_sigma(engine):
 
 
 def test_supplied_normals_reach_both_tensor_kernels(engine, oracle):
-    """MCR_KERNEL_TENSOR with caller-supplied normals: N <= 128 runs the supplied-normals instantiation of the tile kernel
-    (tc_path_kernel<128, 3, 3, true>: same generator hand-over, MMA issue and epilogue code as the headline kernel, the normals read
-    from HBM), N > 128 the streamed kernel.  Ragged trial counts, adversarial normals of very different magnitude, zeros."""
+    """MCR_KERNEL_TENSOR with caller-supplied normals: odd N <= 128 and N < 36 run the supplied-normals instantiation of the tile
+    kernel (tc_path_kernel<128, 3, 3, true>: same generator hand-over, MMA issue and epilogue code as the headline kernel, the
+    normals read from HBM element by element), even N >= 36 and every N > 128 the streamed kernel (even N: through TMA boxes).
+    Ragged trial counts, adversarial normals of very different magnitude, zeros."""
     rng = np.random.default_rng(5)
-    for N, M in ((15, 1), (36, 129), (50, 20_001), (128, 4_097), (129, 1_000), (600, 700)):
+    for N, M in ((15, 1), (34, 300), (36, 129), (50, 20_001), (51, 5_000), (127, 2_000), (128, 4_097), (129, 1_000), (600, 700)):
         m = synthetic_model(N)
         A = engine.upload_sigma(m.mu, m.Sigma)
         Z = rng.standard_normal((M, N))
@@ -275,7 +276,8 @@ def test_supplied_normals_reach_both_tensor_kernels(engine, oracle):
         Z[5::13] = 0.0
         ro = oracle.run_normals(A, m.mu, m.k, m.x, Z)
         r = engine.run_with_normals(Z, m.x, m.k, kernel=api.KERNEL_TENSOR)
-        assert r.kernel == "tensor" and r.padded_N == (128 if N <= 128 else (N + 15) // 16 * 16)
+        tile = N <= 128 and (N % 2 == 1 or N < 36)
+        assert r.kernel == "tensor" and r.padded_N == (128 if tile else (N + 15) // 16 * 16)
         np.testing.assert_array_equal(r.S_values, ro["S_values"])
         assert (r.count, r.sum_S) == (ro["count"], ro["sum_S"])
 
