@@ -740,18 +740,22 @@ __global__ void __launch_bounds__(SUPPLIED ? ST_THREADS_SUPPLIED : ST_THREADS, 1
                                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_zbempty[slot])) : "memory");
                                 ++zk;
                             }
+                            // One fp64 -> fp32 conversion per normal, then the same fp32 split as the generated normals and the tile
+                            // kernel's supplied-normals path (hi = rn16(z), lo = rn16(z - hi): z is represented to 2^-22 |z|, the
+                            // fp32 rounding adds 2^-24 |z|; the guard band's relative part is 2^-18 or more).  Splitting the double
+                            // itself took three fp64 conversions per normal, and the XU pipe they run on bound the kernel (ncu:
+                            // 49 % active over the whole launch, profiles/r02_stream_supplied_ncu_summary.txt).
+                            float z[16];
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
                                 const double zd = ZTMA ? (col0 + q < kend ? zbuf[q] : 0.0) : ((i < p.M && col0 + q < kend) ? __ldg(zrow + col0 + q) : 0.0);
-                                const float zf = (float)zd;
-                                zsq = fmaf(zf, zf, zsq);
-                                // split the fp64 normal itself: hi = rn16(z), lo = rn16(z - hi)
-                                const __half h = __float2half_rn(zf);
-                                const __half l = __float2half_rn((float)(zd - (double)__half2float(h)));
-                                const uint32_t hb = (uint32_t)__half_as_ushort(h), lb = (uint32_t)__half_as_ushort(l);
-                                if (q & 1) { hv[q >> 1] |= hb << 16; lv[q >> 1] |= lb << 16; }
-                                else { hv[q >> 1] = hb; lv[q >> 1] = lb; }
+                                z[q] = (float)zd;
                             }
+                            float2 acc2 = make_float2(zsq, 0.0f);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) acc2 = __ffma2_rn(make_float2(z[2 * q], z[2 * q + 1]), make_float2(z[2 * q], z[2 * q + 1]), acc2);
+                            zsq = acc2.x + acc2.y;
+                            split16(z, hv, lv);
                         } else if ((ps > 0 && kb < KCACHE) || (prefetch && kb == KCACHE)) {
                             // generated (and counted into zsq_cached) in the first pass - or, the first K-block after the cached
                             // ones in the last pass, at the beginning of this pass into the cache slot of K-block 0 (below)
