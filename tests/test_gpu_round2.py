@@ -399,3 +399,35 @@ def test_supplied_normals_streamed_repeatedly(engine, N, mode):
         assert r.kernel == "tensor"
         np.testing.assert_array_equal(r.S_values, exact.S_values)
         assert (r.count, r.sum_S) == (exact.count, exact.sum_S)
+
+
+def test_supplied_normals_tma_edge_cases(engine, oracle):
+    """Supplied normals through the TMA boxes of the streamed kernel: a single trial, one short of a tile, a ragged last K-block at
+    the largest even N, and a device matrix that is NOT 16-byte aligned (the tensor map cannot describe it: element loads)."""
+    import torch
+    rng = np.random.default_rng(11)
+    for N, M in ((600, 1), (600, 127), (64, 1), (130, 129), (1022, 300)):
+        m = synthetic_model(N)
+        A = engine.upload_sigma(m.mu, m.Sigma)
+        Z = rng.standard_normal((M, N))
+        ro = oracle.run_normals(A, m.mu, m.k, m.x, Z)
+        r = engine.run_with_normals(Z, m.x, m.k, kernel=api.KERNEL_TENSOR)
+        assert r.kernel == "tensor" and r.padded_N == (N + 15) // 16 * 16
+        np.testing.assert_array_equal(r.S_values, ro["S_values"])
+        assert (r.count, r.sum_S) == (ro["count"], ro["sum_S"])
+    N, M = 256, 5_000
+    m = synthetic_model(N)
+    A = engine.upload_sigma(m.mu, m.Sigma)
+    Z = rng.standard_normal((M, N))
+    ro = oracle.run_normals(A, m.mu, m.k, m.x, Z)
+    buf = torch.zeros(M * N + 1, dtype=torch.float64, device="cuda")
+    buf[1:] = torch.from_numpy(Z.reshape(-1)).cuda()
+    for off in (0, 1):   # 16-byte aligned copy (TMA) and the copy one double further (element loads)
+        if off == 0:
+            src = buf[1:].clone()
+            assert src.data_ptr() % 16 == 0
+        else:
+            src = buf[1:]
+            assert src.data_ptr() % 16 == 8
+        r = engine.run_with_normals_device(src.data_ptr(), M, m.x, m.k, kernel=api.KERNEL_TENSOR)
+        assert (r.kernel, r.count, r.sum_S) == ("tensor", ro["count"], ro["sum_S"])
