@@ -556,7 +556,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         tl.key0 = key0; tl.key1 = key1; tl.k = k; tl.d_image = e->d_tc_image;
         tl.flag_list = e->d_flag_list; tl.flag_count = e->d_flag_count; tl.flag_cap = FLAG_CAP;
         // (supplied normals: exact_pairs_kernel re-derives its normals from Philox, so every near-threshold trial takes the fp64 kernel)
-        tl.pair_list = (plan.recheck && !sup) ? e->d_pair_list : nullptr; tl.pair_count = e->d_pair_count; tl.pair_cap = PAIR_CAP;
+        tl.pair_list = plan.recheck ? e->d_pair_list : nullptr; tl.pair_count = e->d_pair_count; tl.pair_cap = PAIR_CAP;
         tl.block_partials = e->d_block_partials;
     }
 
@@ -703,9 +703,8 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
         stl.key0 = key0; stl.key1 = key1; stl.N = N; stl.k = k; stl.lower = e->lower ? 1 : 0;
         stl.d_image = e->d_stream_image;
         stl.flag_list = e->d_flag_list; stl.flag_count = e->d_flag_count; stl.flag_cap = FLAG_CAP;
-        // supplied normals: exact_pairs_kernel re-derives its normals from Philox, so every near-threshold trial takes the
-        // whole-trial fp64 kernel (which reads the caller's normals)
-        stl.pair_list = (plan.recheck && !dZ) ? e->d_pair_list : nullptr; stl.pair_count = e->d_pair_count; stl.pair_cap = PAIR_CAP;
+        // (supplied normals: exact_pairs_kernel reads the caller's matrix like the whole-trial kernel does)
+        stl.pair_list = plan.recheck ? e->d_pair_list : nullptr; stl.pair_count = e->d_pair_count; stl.pair_cap = PAIR_CAP;
         stl.block_partials = e->d_block_partials;
     }
 
@@ -773,7 +772,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
                     pp.pair_list = e->d_pair_list; pp.pair_count = e->d_pair_count; pp.pair_cap = PAIR_CAP;
                     pp.path_offset = path_offset + done; pp.key0 = key0; pp.key1 = key1;
                     pp.N = N; pp.lower = e->lower ? 1 : 0; pp.x = x; pp.mu = e->d_mu; pp.A_rm = e->d_Arm;
-                    pp.k = k; pp.S_out = xp.S_out; pp.accum = e->d_accum; pp.mode = 2;
+                    pp.k = k; pp.S_out = xp.S_out; pp.accum = e->d_accum; pp.mode = 2; pp.Z = xp.Z;
                     MCR_CUDA(launch_exact_pairs(pp, e->num_sms, s));
                     ++launches;
                     fin.pair_count = e->d_pair_count; fin.pair_cap = PAIR_CAP;
@@ -820,7 +819,7 @@ int enqueue_run(mcr_engine* e, uint64_t M, uint64_t path_offset, uint64_t seed, 
                 pp.pair_list = e->d_pair_list; pp.pair_count = e->d_pair_count; pp.pair_cap = PAIR_CAP;
                 pp.path_offset = path_offset + done; pp.key0 = key0; pp.key1 = key1;
                 pp.N = N; pp.lower = e->lower ? 1 : 0; pp.x = x; pp.mu = e->d_mu; pp.A_rm = e->d_Arm;
-                pp.k = k; pp.S_out = xp.S_out; pp.accum = e->d_accum; pp.mode = 1;
+                pp.k = k; pp.S_out = xp.S_out; pp.accum = e->d_accum; pp.mode = 1; pp.Z = xp.Z;
                 MCR_CUDA(launch_exact_pairs(pp, e->num_sms, s));
                 ++launches;
                 fin.pair_count = e->d_pair_count; fin.pair_cap = PAIR_CAP;

@@ -282,12 +282,17 @@ __global__ void __launch_bounds__(128) exact_pairs_kernel(const PairParams p) {
         const int jend = p.lower ? row + 1 : p.N;
         const double* a = p.A_rm + (size_t)row * p.N;
         double acc = 0.0;
-        for (int b = 0; 4 * b < jend; ++b) {
-            float zf[4];
-            normals4((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)b, p.key0, p.key1, zf);
+        if (p.Z) {   // the caller's normals: the same products in the same order as exact_kernel's row
+            const double* z = p.Z + (size_t)i * (size_t)p.N;
+            for (int j = 0; j < jend; ++j) acc = __dadd_rn(acc, __dmul_rn(__ldg(z + j), __ldg(a + j)));
+        } else {
+            for (int b = 0; 4 * b < jend; ++b) {
+                float zf[4];
+                normals4((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)b, p.key0, p.key1, zf);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (4 * b + q < jend) acc = __dadd_rn(acc, __dmul_rn((double)zf[q], __ldg(a + 4 * b + q)));
+                for (int q = 0; q < 4; ++q)
+                    if (4 * b + q < jend) acc = __dadd_rn(acc, __dmul_rn((double)zf[q], __ldg(a + 4 * b + q)));
+            }
         }
         double R = __dadd_rn(0.0, __dmul_rn(1.0, acc));
         R = __dadd_rn(R, p.mu[row]);

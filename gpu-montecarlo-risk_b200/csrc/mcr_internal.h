@@ -85,6 +85,7 @@ struct PairParams {
     double x;
     const double* mu;
     const double* A_rm;                    // N x N row-major fp64
+    const double* Z;                       // supplied normals (M x N fp64, chunk-relative like the trial indices) or nullptr: Philox
     uint16_t* S_acc;                       // mode 0: hit added here (two trials per 32-bit word)
     int32_t k;                             // modes 1, 2: S = S_rest + hit is final: counted into accum like exact_kernel does
     int32_t* S_out;
