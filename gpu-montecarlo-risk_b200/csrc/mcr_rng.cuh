@@ -171,78 +171,6 @@ struct PhiloxPath {
             box_muller(c2[t], c3[t], z[4 * t + 2], z[4 * t + 3]);
         }
     }
-    // the raw words of NB consecutive blocks (rounds interleaved like normals_multi): w[4 t .. 4 t + 3] = block b + t.  Lets a
-    // caller overlap the Philox rounds of its NEXT blocks (heavy FMA pipe) with the Box-Muller of the current ones (XU pipe)
-    template <int NB>
-    __device__ __forceinline__ void words_multi(uint32_t b, uint32_t k0, uint32_t k1, uint32_t* w) const {
-        uint32_t c0[NB], c1[NB], c2[NB], c3[NB];
-        uint32_t ka = k0 + PHILOX_W0, kb = k1 + PHILOX_W1;   // round-2 keys
-#pragma unroll
-        for (int t = 0; t < NB; ++t) {
-            const uint64_t p1 = (uint64_t)PHILOX_M1 * (b + t);
-            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ path_hi ^ k0;
-            const uint32_t n1 = (uint32_t)p1;
-            const uint64_t q0 = (uint64_t)PHILOX_M0 * n0;
-            c0[t] = p1p_hi ^ n1 ^ ka;
-            c1[t] = p1p_lo;
-            c2[t] = (uint32_t)(q0 >> 32) ^ n3 ^ kb;
-            c3[t] = (uint32_t)q0;
-        }
-#pragma unroll
-        for (int r = 2; r < 10; r++) {
-            ka += PHILOX_W0; kb += PHILOX_W1;
-#pragma unroll
-            for (int t = 0; t < NB; ++t) {
-                const uint64_t a0 = (uint64_t)PHILOX_M0 * c0[t];
-                const uint64_t a1 = (uint64_t)PHILOX_M1 * c2[t];
-                const uint32_t m0 = (uint32_t)(a1 >> 32) ^ c1[t] ^ ka;
-                const uint32_t m2 = (uint32_t)(a0 >> 32) ^ c3[t] ^ kb;
-                c1[t] = (uint32_t)a1;
-                c3[t] = (uint32_t)a0;
-                c0[t] = m0;
-                c2[t] = m2;
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < NB; ++t) { w[4 * t] = c0[t]; w[4 * t + 1] = c1[t]; w[4 * t + 2] = c2[t]; w[4 * t + 3] = c3[t]; }
-    }
-    // words_multi<4> of blocks b .. b + 3 with the Box-Muller of 16 EARLIER words (u_in -> z_out) woven in: one pair of normals
-    // after each of the eight unrolled rounds, so that the multiplies (heavy FMA pipe) and the MUFU / I2F work (XU pipe) of a
-    // thread alternate in program order instead of forming two long single-pipe phases
-    __device__ __forceinline__ void words4_boxmuller16(uint32_t b, uint32_t k0, uint32_t k1, uint32_t* w, const uint32_t* u_in, float* z_out) const {
-        constexpr int NB = 4;
-        uint32_t c0[NB], c1[NB], c2[NB], c3[NB];
-        uint32_t ka = k0 + PHILOX_W0, kb = k1 + PHILOX_W1;   // round-2 keys
-#pragma unroll
-        for (int t = 0; t < NB; ++t) {
-            const uint64_t p1 = (uint64_t)PHILOX_M1 * (b + t);
-            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ path_hi ^ k0;
-            const uint32_t n1 = (uint32_t)p1;
-            const uint64_t q0 = (uint64_t)PHILOX_M0 * n0;
-            c0[t] = p1p_hi ^ n1 ^ ka;
-            c1[t] = p1p_lo;
-            c2[t] = (uint32_t)(q0 >> 32) ^ n3 ^ kb;
-            c3[t] = (uint32_t)q0;
-        }
-#pragma unroll
-        for (int r = 2; r < 10; r++) {
-            ka += PHILOX_W0; kb += PHILOX_W1;
-#pragma unroll
-            for (int t = 0; t < NB; ++t) {
-                const uint64_t a0 = (uint64_t)PHILOX_M0 * c0[t];
-                const uint64_t a1 = (uint64_t)PHILOX_M1 * c2[t];
-                const uint32_t m0 = (uint32_t)(a1 >> 32) ^ c1[t] ^ ka;
-                const uint32_t m2 = (uint32_t)(a0 >> 32) ^ c3[t] ^ kb;
-                c1[t] = (uint32_t)a1;
-                c3[t] = (uint32_t)a0;
-                c0[t] = m0;
-                c2[t] = m2;
-            }
-            box_muller(u_in[2 * (r - 2)], u_in[2 * (r - 2) + 1], z_out[2 * (r - 2)], z_out[2 * (r - 2) + 1]);
-        }
-#pragma unroll
-        for (int t = 0; t < NB; ++t) { w[4 * t] = c0[t]; w[4 * t + 1] = c1[t]; w[4 * t + 2] = c2[t]; w[4 * t + 3] = c3[t]; }
-    }
     __device__ __forceinline__ void normals(uint32_t b, uint32_t k0, uint32_t k1, float z[4]) const {
         const u32x4 u = block(b, k0, k1);
         box_muller(u.x, u.y, z[0], z[1]);
