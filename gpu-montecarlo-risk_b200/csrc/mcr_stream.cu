@@ -337,7 +337,8 @@ __global__ void __launch_bounds__(SUPPLIED ? ST_THREADS_SUPPLIED : ST_THREADS, 1
         mbar_init(&s_done, 1);
         for (int b = 0; b < ST_ZSLOTS; ++b) mbar_init(&s_zfull[b], 2 * ST_GEN_THREADS / 32);   // one arrival per generator warp of the pair
         mbar_init(&s_accfree, 2 * ST_GEN_THREADS / 32);
-        for (int b = 0; b < ST_ZBOX; ++b) { mbar_init(&s_zbfull[b], 1); mbar_init(&s_zbempty[b], 4); }
+        if (SUPPLIED)
+            for (int b = 0; b < ST_ZBOX; ++b) { mbar_init(&s_zbfull[b], 1); mbar_init(&s_zbempty[b], 4); }
     }
     if (PORT)
         for (int t = tid; t < MCR_PORTFOLIO_BINS; t += ST_THREADS) s_hist[t] = 0ull;
