@@ -98,20 +98,14 @@ constexpr int ST_GEN_THREADS = 128 * ST_PARTS;
 constexpr int ST_THREADS = ST_GEN_THREADS + 64;      // + MMA-issue warp + transform loader warp
 constexpr int ST_THREADS_SUPPLIED = ST_THREADS + 32; // + Z loader warp (the supplied-normals instantiation only)
 constexpr int ST_MMA_WARP = ST_GEN_THREADS / 32, ST_LOAD_WARP = ST_MMA_WARP + 1, ST_ZLOAD_WARP = ST_MMA_WARP + 2;
-// supplied normals: TMA boxes (16 columns x 128 trials of fp64, 16 KB each), ST_ZDEPTH per generator part.  Every box slot belongs to
+// supplied normals: TMA boxes (16 columns x 128 trials of fp64, 16 KB each), one or two per generator part.  Every box slot belongs to
 // ONE part: its four warps take the slot's uses in order, so a parity wait is never more than one phase ahead (boxes land out of
 // order; with slots shared between parts a fast warp could wait for use u + 1 of a slot whose use u has not landed yet, and a
-// parity wait two phases ahead passes at once).
-#ifndef MCR_STREAM_ZDEPTH
-#define MCR_STREAM_ZDEPTH 2
-#endif
-constexpr int ST_ZDEPTH = MCR_STREAM_ZDEPTH;
-constexpr int ST_ZBOX = ST_PARTS * ST_ZDEPTH;
+// parity wait two phases ahead passes at once).  Shared memory is split between the boxes and the ring of transform pieces:
+// single-pass models (N <= 384) are bound by the stream of normals - two boxes per part, two pieces (N = 256: 4.5 against 4.1 TB/s);
+// models of several passes also need their transform stream - one box per part, four pieces (N = 600: 2.6 against 2.3 TB/s).
+constexpr int ST_ZBOX_MAX = ST_PARTS * 2;
 constexpr uint32_t ST_ZBOX_BYTES = 16 * 128 * 8;
-#ifndef MCR_STREAM_ZRING
-#define MCR_STREAM_ZRING (MCR_STREAM_ZDEPTH >= 2 ? 2 : 4)
-#endif
-constexpr int ST_ZRING = MCR_STREAM_ZRING;           // ... next to which the transform ring keeps two (four) 32 KB pieces
 constexpr int ST_ALL = ST_GEN_THREADS + 32;          // generators + MMA warp
 constexpr int ST_BAR_SLOT = 1, ST_BAR_ACC = 3, ST_BAR_GEN = 4;   // named barriers: 1, 2 = Z slot full; accumulators free; generators only
 constexpr uint32_t ST_KEY_MASK = 0xFFFFFC00u;        // epilogue keys: bits 10.. = |accumulator| << 1 (truncated), 1..9 = column, 0 = sign
@@ -132,6 +126,7 @@ struct StreamParams {
     size_t image_rank_bytes;   // CTA-pair form: the image is [halves of CTA 0][halves of CTA 1], this many bytes each
     const double* Z;           // SUPPLIED: M x N fp64 row-major (chunk-relative), else nullptr
     int32_t ztma;              // SUPPLIED: 1 = Z is read through the tensor map (second kernel parameter), 0 = element loads
+    int32_t zbox_shift;        // ... into 1 << zbox_shift box slots (4 or 8: one or two per generator part)
     int32_t* S_out;
     uint32_t* flag_list;
     uint32_t* flag_count;
@@ -315,7 +310,7 @@ __global__ void __launch_bounds__(SUPPLIED ? ST_THREADS_SUPPLIED : ST_THREADS, 1
     // PAIR, used in the leader only: Z slot written / accumulators read out by the generators of both CTAs; CTA 1's half piece arrived
     __shared__ uint64_t s_zfull[ST_ZSLOTS], s_accfree, s_bpeer[ST_RING_SLOTS];
     // SUPPLIED through TMA: the ring of Z boxes behind the transform ring; filled by the Z loader, each read by the four warps of a part
-    __shared__ uint64_t s_zbfull[ST_ZBOX], s_zbempty[ST_ZBOX];
+    __shared__ uint64_t s_zbfull[ST_ZBOX_MAX], s_zbempty[ST_ZBOX_MAX];
     uint8_t* const s_zbox = s_ring + (size_t)RING * PIECE;
     const bool ZTMA = SUPPLIED && p.ztma != 0;
     __shared__ uint32_t s_tmem;
@@ -338,7 +333,7 @@ __global__ void __launch_bounds__(SUPPLIED ? ST_THREADS_SUPPLIED : ST_THREADS, 1
         for (int b = 0; b < ST_ZSLOTS; ++b) mbar_init(&s_zfull[b], 2 * ST_GEN_THREADS / 32);   // one arrival per generator warp of the pair
         mbar_init(&s_accfree, 2 * ST_GEN_THREADS / 32);
         if (SUPPLIED)
-            for (int b = 0; b < ST_ZBOX; ++b) { mbar_init(&s_zbfull[b], 1); mbar_init(&s_zbempty[b], 4); }
+            for (int b = 0; b < ST_ZBOX_MAX; ++b) { mbar_init(&s_zbfull[b], 1); mbar_init(&s_zbempty[b], 4); }
     }
     if (PORT)
         for (int t = tid; t < MCR_PORTFOLIO_BINS; t += ST_THREADS) s_hist[t] = 0ull;
@@ -499,7 +494,7 @@ __global__ void __launch_bounds__(SUPPLIED ? ST_THREADS_SUPPLIED : ST_THREADS, 1
                 for (int ps = 0; ps < NPASS; ++ps)
                     for (int kb = 0; kb < p.pass[ps].kbn; ++kb)
                         for (int part = 0; part < ST_PARTS; ++part, ++seq) {
-                            const uint32_t slot = seq % ST_ZBOX, use = seq / ST_ZBOX;   // (slot % ST_PARTS == part)
+                            const uint32_t slot = seq & ((1u << p.zbox_shift) - 1u), use = seq >> p.zbox_shift;   // (slot % ST_PARTS == part)
                             if (use > 0) mbar_wait<20>(&s_zbempty[slot], (use - 1u) & 1u);
                             mbar_expect_tx_st(&s_zbfull[slot], ST_ZBOX_BYTES);
                             tma_load_2d(smem_u32(s_zbox + (size_t)slot * ST_ZBOX_BYTES), &zmap, KBLOCK * kb + 16 * part, r0, &s_zbfull[slot]);
@@ -722,8 +717,8 @@ __global__ void __launch_bounds__(SUPPLIED ? ST_THREADS_SUPPLIED : ST_THREADS, 1
                             double zbuf[16];
                             if (ZTMA) {
                                 // this part's box: row = trial, 128 bytes = 16 doubles, 16-byte chunk c stored at c ^ (row % 8)
-                                const uint32_t seq = 4u * zk + (uint32_t)part, slot = seq % ST_ZBOX;
-                                mbar_wait<20>(&s_zbfull[slot], (seq / ST_ZBOX) & 1u);
+                                const uint32_t seq = 4u * zk + (uint32_t)part, slot = seq & ((1u << p.zbox_shift) - 1u);
+                                mbar_wait<20>(&s_zbfull[slot], (seq >> p.zbox_shift) & 1u);
                                 const uint8_t* brow = s_zbox + (size_t)slot * ST_ZBOX_BYTES + (size_t)row * 128;
 #pragma unroll
                                 for (int c = 0; c < 8; ++c) {
@@ -1045,8 +1040,12 @@ cudaError_t stream_launch(const StreamLaunch& l, int num_sms, cudaStream_t s) {
     alignas(64) CUtensorMap zmap;
     memset(&zmap, 0, sizeof(zmap));
     static const bool no_ztma = [] { const char* v = getenv("MCR_STREAM_NO_ZTMA"); return v && *v && atoi(v) != 0; }();   // A/B runs
-    if (l.d_Z && !no_ztma && encode_z_map(l.d_Z, l.M, l.N, &zmap)) { p.ztma = 1; p.ring = ST_ZRING; }
-    const size_t smem = p.ztma ? (size_t)ST_ZRING * ST_PIECE_MAX + (size_t)ST_ZBOX * ST_ZBOX_BYTES + 1024 : (size_t)(ST_RING_MAX - p.kcache) * ST_PIECE_MAX + (size_t)p.kcache * ST_ZCACHE_BYTES + 1024 + (l.portfolio ? (size_t)MCR_PORTFOLIO_BINS * 8 : 0);
+    if (l.d_Z && !no_ztma && encode_z_map(l.d_Z, l.M, l.N, &zmap)) {
+        p.ztma = 1;
+        p.zbox_shift = p.npass > 1 ? 2 : 3;   // one box per part and four transform pieces, or two and two (see ST_ZBOX_MAX)
+        p.ring = p.npass > 1 ? 4 : 2;
+    }
+    const size_t smem = p.ztma ? (size_t)p.ring * ST_PIECE_MAX + ((size_t)ST_ZBOX_BYTES << p.zbox_shift) + 1024 : (size_t)(ST_RING_MAX - p.kcache) * ST_PIECE_MAX + (size_t)p.kcache * ST_ZCACHE_BYTES + 1024 + (l.portfolio ? (size_t)MCR_PORTFOLIO_BINS * 8 : 0);
     p.portfolio = l.portfolio;
     if (l.portfolio) {
         p.port_col = l.N - p.pass[p.npass - 1].r0;
