@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Timeline of one tile of the streamed kernel from a -DMCR_STREAM_TRACE=1 build (tools/devbuild_one.sh trace mcr_stream -DMCR_STREAM_TRACE=1):
-    MCR_B200_LIB=devlibs/trace/libmcr_b200.so python tools/stream_trace.py [N] [tile]"""
+    MCR_B200_LIB=devlibs/trace/libmcr_b200.so python tools/stream_trace.py [N] [tile] [supplied]"""
 import ctypes as C
 import sys
 from pathlib import Path
@@ -12,17 +12,24 @@ from mcr_b200.synthetic import synthetic_model
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 600
 tile = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+supplied = len(sys.argv) > 3 and sys.argv[3] == "supplied"   # caller-supplied normals (TMA boxes) instead of Philox
 m = synthetic_model(N)
 e = api.Engine(0)
 e.upload_sigma(m.mu, m.Sigma)
 M = 148 * 128 * 12
-e.run(M, 67, m.x, m.k, no_recheck=True)
+if supplied:
+    import torch
+    Zd = torch.randn(M, N, dtype=torch.float64, device="cuda")
+    run = lambda: e.run_with_normals_device(Zd.data_ptr(), M, m.x, m.k, kernel=api.KERNEL_TENSOR, no_recheck=True)
+else:
+    run = lambda: e.run(M, 67, m.x, m.k, no_recheck=True)
+run()
 lib = _lib.load()
 ROLES, CAP = 4, 16384
 buf = np.zeros(ROLES * CAP, np.uint64)
 cnt = np.zeros(ROLES, np.uint32)
 lib.mcr_stream_trace_dump(buf.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 1)   # drop the warm-up run
-e.run(M, 67, m.x, m.k, no_recheck=True)
+run()
 assert lib.mcr_stream_trace_dump(buf.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 1) == 0
 names = {0: "gen w0 ", 1: "gen w12", 2: "mma    ", 3: "loader "}
 tags = {0: {1: "step begins", 2: "normals ready", 3: "slot free", 4: "handed over", 5: "epilogue begins", 6: "epilogue done", 7: "pass MMAs complete"},
