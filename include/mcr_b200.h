@@ -163,7 +163,10 @@ int mcr_result_from_partials_ext(const uint64_t *h_partials, const uint64_t *h_e
 
 /* Parity entry point (the model interface has no "feed normals" hook):
  * same correlate/threshold/reduce code, normals supplied by the caller instead of Philox.
- * Z: HOST pointer, M x N row-major fp64 (the layout serial.c:67-69 fills, one trial per row). */
+ * Z: HOST pointer, M x N row-major fp64 (the layout serial.c:67-69 fills, one trial per row).
+ * Kernel choice under MCR_KERNEL_AUTO: the FFMA2 kernel for N < 64 and for odd N <= 128, the streamed tcgen05 kernel otherwise
+ * (even N: it reads the matrix through a 2-D TMA tensor map, which needs 16-byte aligned rows; any other matrix is read
+ * element by element, slower but identical).  Portfolio outputs are not available in this mode. */
 int mcr_run_with_normals(mcr_engine *e, uint64_t M, const double *Z, double x, int k,
                          const mcr_run_options *opt, int32_t *S_values_host /* M int32 or NULL */,
                          mcr_result *out);
