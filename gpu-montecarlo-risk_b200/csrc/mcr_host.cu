@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <condition_variable>
 #include <functional>
 #include <map>
 #include <mutex>
@@ -142,6 +143,53 @@ static void widen_S(const T* src, int32_t* dst, uint64_t n) {
 
 using namespace mcr;
 
+// One host thread per device, kept for the life of the process (a call used to start and join its threads twice: ~0.2 ms of a
+// 5.6 ms run on 8 GPUs).  Worker g sleeps on a condition variable until run() hands it `job(g)`.  The pool is never destroyed
+// (no static destructor runs while workers wait); calls are serialised by g_host_mu.
+namespace {
+class DeviceWorkers {
+public:
+    void run(int n, const std::function<void(int)>& job) {
+        std::unique_lock<std::mutex> lk(mu_);
+        while ((int)threads_ < n) {
+            const int g = threads_++;
+            std::thread([this, g]() { loop(g); }).detach();
+        }
+        job_ = &job;
+        pending_ = n;
+        ++generation_;
+        want_ = n;
+        cv_work_.notify_all();
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void loop(int g) {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_work_.wait(lk, [&] { return generation_ != seen && g < want_; });
+            seen = generation_;
+            const std::function<void(int)>* job = job_;
+            lk.unlock();
+            (*job)(g);
+            lk.lock();
+            if (--pending_ == 0) cv_done_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(int)>* job_ = nullptr;
+    uint64_t generation_ = 0;
+    int threads_ = 0, pending_ = 0, want_ = 0;
+};
+DeviceWorkers& device_workers() {
+    static DeviceWorkers* w = new DeviceWorkers();   // leaked on purpose
+    return *w;
+}
+}  // namespace
+
 extern "C" int mcr_simulate_host(const mcr_host_request* req, mcr_result* out) {
     if (!req || !out) return fail("mcr_simulate_host: null argument");
     if (req->struct_size != sizeof(mcr_host_request)) return fail("mcr_simulate_host: struct_size mismatch (ABI)");
@@ -176,13 +224,10 @@ extern "C" int mcr_simulate_host(const mcr_host_request* req, mcr_result* out) {
         if (n == 1) return work(0);
         std::vector<int> rcs(n, 0);
         std::vector<std::string> msgs(n);
-        std::vector<std::thread> th;
-        for (int g = 0; g < n; ++g)
-            th.emplace_back([&, g]() {
-                rcs[g] = work(g);
-                if (rcs[g]) msgs[g] = mcr_last_error();
-            });
-        for (auto& t : th) t.join();
+        device_workers().run(n, [&](int g) {
+            rcs[g] = work(g);
+            if (rcs[g]) msgs[g] = mcr_last_error();
+        });
         for (int g = 0; g < n; ++g)
             if (rcs[g]) return fail("%s", msgs[g].c_str());
         return 0;
