@@ -37,7 +37,7 @@ int main(int argc, char **argv) {
     const McrHostAllocator pinned = {mcr_host_alloc_pinned, mcr_host_free_pinned};
     if (mcr_load_host_model_ex(mu_path, sigma_path, &pinned, &m) != 0) return 1;
 
-    double *A = (double *)malloc((size_t)m.N * m.N * sizeof(double));
+    double *A = (double *)malloc((size_t)m.N * (size_t)m.N * sizeof(double));
     if (!A || mcr_build_transform(m.Sigma, m.N, m.N, mode, A) != 0) {
         fprintf(stderr, "Error: %s\n", A ? mcr_last_error() : "out of memory");
         mcr_free_host_model(&m);
